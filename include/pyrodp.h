@@ -1,0 +1,173 @@
+/*
+ * pyrodp.h — C ABI of the B200 grid dynamic-programming (value-iteration) engine.
+ *
+ * This is the drop-in boundary for ONE hot path of SherbyRobotics/pyro: the Bellman sweep of
+ * pyro.planning.dynamicprogramming.DynamicProgramming over
+ * pyro.planning.discretizer.GridDynamicSystem.  pyro has no FFI; its extension point is
+ * subclassing DynamicProgramming and overriding the three per-sweep hooks
+ * (pyro/planning/dynamicprogramming.py:175 initialize_backward_step, :195/:557
+ * compute_backward_step, :240 finalize_backward_step).  The functions below are exactly what
+ * such a subclass binds through ctypes (see INTEGRATION.md for the stub).
+ *
+ * Conventions
+ *   - plain C, no CUDA/torch types in any signature; device pointers and streams travel as void*.
+ *   - every function returns 0 on success, a negative PDP_E* code on failure;
+ *     pdp_last_error() gives the message (handle may be NULL for creation errors).
+ *   - host arrays are borrowed for the duration of the call only; the handle owns device memory.
+ *   - node ids are C order of x_grid_dim (last axis fastest), action ids C order of u_grid_dim,
+ *     as pyro/planning/discretizer.py:167-310 enumerates them.
+ *   - one handle = one caller thread = one GPU (the current CUDA device at pdp_create).
+ *   - there is NO CPU fallback: if no CUDA device is usable pdp_create fails with PDP_ECUDA.
+ */
+#ifndef PYRODP_H
+#define PYRODP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDP_ABI_VERSION 1
+#define PDP_MAX_N 4 /* state dims supported by pyro's grid (discretizer.py:183-245: n in {2,3,4}) */
+#define PDP_MAX_M 2 /* input dims supported (discretizer.py:271-306: m in {1,2}) */
+
+/* error codes */
+#define PDP_OK 0
+#define PDP_EINVAL (-1)  /* bad argument / size mismatch   -> Python ValueError            */
+#define PDP_ENOTSUP (-2) /* unsupported dims / system       -> Python NotImplementedError   */
+#define PDP_ECUDA (-3)   /* CUDA runtime failure (sticky)   -> Python RuntimeError          */
+#define PDP_ESTATE (-4)  /* call order violated (e.g. sweep before set_J)                   */
+
+/* system_id: which closed-form f(x,u) the fused kernel evaluates on the fly */
+#define PDP_SYS_LUT 0      /* no fused dynamics: sweeps use uploaded x_next/G tables (dynamicprogramming.py:557-570) */
+#define PDP_SYS_PENDULUM 1 /* 1-dof MechanicalSystem, n=2,m=1   (pyro/dynamic/pendulum.py:16 SinglePendulum)       */
+#define PDP_SYS_TWOLINK 2  /* 2-link arm form, n=4,m=2 (pendulum.py:340 DoublePendulum, manipulator.py:795 TwoLinkManipulator) */
+#define PDP_SYS_CARTPOLE 3 /* cart + pole, n=4,m=1              (pyro/dynamic/cartpole.py:322 CartPole)              */
+
+/* cost_id: which stage cost g(x,u) / terminal cost h(x) */
+#define PDP_COST_QUADRATIC 1 /* pyro/analysis/costfunction.py:100-204 QuadraticCostFunction */
+#define PDP_COST_TIME 2      /* pyro/analysis/costfunction.py:287-334 TimeCostFunction      */
+
+/*
+ * Problem descriptor (POD).  Everything a sweep needs, read by the host shim from the pyro
+ * objects lazily at the first sweep (grid_sys, grid_sys.sys, cf, dp.alpha).
+ *
+ * Transcendentals and LAPACK results are NOT recomputed on the device: the shim tabulates them
+ * per grid level with the very NumPy calls the reference makes (np.sin, np.cos, np.linalg.inv),
+ * so those bits are identical by construction (hard part 1).
+ *
+ * sys_tab / sys_par layout per system_id (all float64, host pointers, copied at pdp_create):
+ *  PENDULUM : sys_tab[0][dims[0]]        = gravity torque g(q_i)   (pendulum.py:126-137)
+ *             sys_par[0] = inv(H)[0,0] (mechanical.py:231), sys_par[1] = d1 (pendulum.py:141-150)
+ *  TWOLINK  : sys_tab[0][dims[1]*4]      = inv(H(q1_j)) row-major  (pendulum.py:400-417 / manipulator.py:897-918)
+ *             sys_tab[1][dims[1]]        = h(q1_j)=m2*l1*lc2*sin q1 (pendulum.py:434 / manipulator.py:933)
+ *             sys_tab[2][dims[0]*dims[1]*2] = g(q0_i,q1_j)          (pendulum.py:465-473 / manipulator.py:964-972)
+ *             sys_par[0] = d1, sys_par[1] = d2                      (pendulum.py:477-493 / manipulator.py:978-992)
+ *  CARTPOLE : sys_tab[0][dims[1]*4]      = inv(H(theta_j))          (cartpole.py:369-384)
+ *             sys_tab[1][dims[1]]        = -m2*lcg*sin(theta_j)     (cartpole.py:399; times theta_dot on device)
+ *             sys_tab[2][dims[1]]        = m2*g*lcg*sin(theta_j)    (cartpole.py:426)
+ * bu[A*dof]  = np.dot(B, u_a) per action (mechanical.py:231), dof = n/2.
+ * gu[A]      = du^T R du per action (costfunction.py:191), 0 for the time cost.
+ * act_ok[A]  = isavalidinput(u_a) box test (pyro/dynamic/system.py:208-215), 1 = allowed.
+ */
+typedef struct pdp_problem {
+    int32_t abi_version; /* PDP_ABI_VERSION */
+    int32_t n;           /* state dimension, 2..4 */
+    int32_t m;           /* input dimension, 1..2 */
+    int32_t system_id;   /* PDP_SYS_* */
+    int32_t cost_id;     /* PDP_COST_* */
+    int32_t ontarget_check; /* costfunction.py:134 */
+    int32_t slab_begin;  /* axis-0 planes [slab_begin, slab_end) are computed by this handle;   */
+    int32_t slab_end;    /* 0, dims[0] on a single GPU (multi-GPU: SURVEY.md 8e)                  */
+    int32_t alloc_planes; /* axis-0 planes to allocate for the J buffers; 0 = dims[0].  A multi-GPU
+                             host sets W*ceil(dims[0]/W) so an equal-count in-place all-gather fits */
+    int32_t reserved0;
+    int32_t dims[PDP_MAX_N];  /* x_grid_dim (discretizer.py:91)  */
+    int32_t udims[PDP_MAX_M]; /* u_grid_dim (discretizer.py:92)  */
+    const double* x_level[PDP_MAX_N]; /* np.linspace levels verbatim (discretizer.py:142) */
+    const double* u_level[PDP_MAX_M]; /* (discretizer.py:158) */
+    double x_lb[PDP_MAX_N], x_ub[PDP_MAX_N]; /* sys.x_lb / x_ub used by isavalidstate (system.py:198-205) */
+    double dt;    /* grid_sys.dt  */
+    double alpha; /* dp.alpha (dynamicprogramming.py:130) */
+    double INF;   /* cf.INF (costfunction.py:32) */
+    double EPS;   /* cf.EPS (costfunction.py:33) */
+    double Q[PDP_MAX_N * PDP_MAX_N]; /* row-major n x n stage weights  (costfunction.py:129) */
+    double S[PDP_MAX_N * PDP_MAX_N]; /* row-major n x n terminal weights (costfunction.py:131) */
+    double xbar[PDP_MAX_N];          /* cf.xbar */
+    double sys_par[8];
+    const double* sys_tab[4];
+    int64_t sys_tab_len[4];
+    const double* bu;      /* [A * n/2] */
+    const double* gu;      /* [A] */
+    const uint8_t* act_ok; /* [A] */
+} pdp_problem;
+
+typedef struct pdp_handle pdp_handle;
+
+/* per-sweep convergence statistics, what finalize_backward_step prints/returns
+ * (dynamicprogramming.py:247-261): max J, max(J - J_next), min(J - J_next), over this handle's slab */
+typedef struct pdp_stats {
+    double j_max;
+    double delta_max;
+    double delta_min;
+} pdp_stats;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+int pdp_abi_version(void);
+int pdp_create(const pdp_problem* p, pdp_handle** out);
+int pdp_destroy(pdp_handle* h);
+const char* pdp_last_error(const pdp_handle* h);
+/* Use an externally owned cudaStream_t for all work of this handle (default: a private stream). */
+int pdp_set_stream(pdp_handle* h, void* cuda_stream);
+
+/* ---- cost-to-go state ---------------------------------------------------------------------
+ * J is the latest cost-to-go (N doubles), pi the latest policy (N int64), J_next the previous J
+ * (dynamicprogramming.py:181-185).  */
+/* replaces DynamicProgramming.evaluate_terminal_cost (dynamicprogramming.py:159-171): J = h(x, tf), pi = 0, on device */
+int pdp_eval_terminal_cost(pdp_handle* h);
+/* upload a full J (N doubles, host), e.g. terminal cost computed by the caller or load_J_next (:489-499) */
+int pdp_set_J(pdp_handle* h, const double* J_host);
+int pdp_get_J(pdp_handle* h, double* J_host);       /* N doubles  */
+int pdp_get_J_next(pdp_handle* h, double* J_host);  /* N doubles  */
+int pdp_get_pi(pdp_handle* h, int64_t* pi_host);    /* N int64    */
+
+/* ---- the hot path ---------------------------------------------------------------------------
+ * replaces initialize_backward_step + compute_backward_step + the reductions of
+ * finalize_backward_step (dynamicprogramming.py:175-261), n_sweeps times back to back on the
+ * device.  stats_out (host, may be NULL) receives n_sweeps entries.  Blocking. */
+int pdp_sweep(pdp_handle* h, int32_t n_sweeps, pdp_stats* stats_out);
+
+/* LUT mode (system_id == PDP_SYS_LUT): the generic, bit-exact path for arbitrary user systems.
+ * x_next: (N_slab, A, n) float64 as discretizer.py:349, G: (N_slab, A) float64 as
+ * dynamicprogramming.py:523 (INF already folded in).  Uploaded once, then pdp_sweep() runs
+ * dynamicprogramming.py:564-570 on the device. */
+int pdp_set_lut(pdp_handle* h, const double* x_next_host, const double* G_host);
+
+/* ---- step after the sweep: policy -> input tables (discretizer.py:616-633 get_input_from_policy),
+ * u_k[s] = input_from_action_id[pi[s], k], computed on the device, N doubles to host */
+int pdp_get_input_from_policy(pdp_handle* h, int32_t k, double* uk_host);
+/* clean_infeasible_set (dynamicprogramming.py:322-334) on the device */
+int pdp_clean_infeasible_set(pdp_handle* h, double tol, int64_t default_action);
+
+/* ---- multi-GPU plumbing (one process per GPU; the host layer does the exchange) -------------
+ * One asynchronous sweep of this handle's slab on its stream, no host sync.  The new J of the
+ * slab is written in place into the full-size "new" buffer; the caller then all-gathers that
+ * buffer across ranks (NCCL) and calls pdp_commit_sweep() to swap J/J_next. */
+int pdp_sweep_async(pdp_handle* h);
+int pdp_commit_sweep(pdp_handle* h);
+/* device pointers: J (N_pad doubles, current), J_new (N_pad doubles, being written), pi (N int64),
+ * stats (3 doubles of the last async sweep: j_max, delta_max, delta_min over the slab) */
+int pdp_device_buffers(pdp_handle* h, void** J_cur, void** J_new, void** pi, void** stats);
+int64_t pdp_nodes(const pdp_handle* h);        /* N = prod(dims) */
+int64_t pdp_nodes_padded(const pdp_handle* h); /* N_pad: allocation size of the J buffers */
+int64_t pdp_actions(const pdp_handle* h);      /* A = prod(udims) */
+/* number of sweep-kernel launches issued by this handle so far (bench.py gpu_launches) */
+int64_t pdp_launch_count(const pdp_handle* h);
+/* device time in ms of the last pdp_sweep() call, measured with CUDA events on the handle's stream */
+double pdp_last_sweep_ms(const pdp_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYRODP_H */

@@ -1,0 +1,293 @@
+"""Drop-in value-iteration planner: the reference's DynamicProgramming API over the B200 engine.
+
+Mirrors pyro/planning/dynamicprogramming.py:
+  DynamicProgramming.__init__(grid_sys, cost_function, final_time=0)          :119
+  initialize_backward_step / compute_backward_step / finalize_backward_step   :175 / :195 / :240
+  compute_steps(n, animate_cost2go, animate_policy, k)                         :265
+  solve_bellman_equation(tol, animate_cost2go, animate_policy, k)              :283
+  clean_infeasible_set(tol)                                                    :322
+  get_lookup_table_controller()                                                :472
+  save_latest(name) / load_J_next(name)                                        :481 / :489
+  DynamicProgrammingWithLookUpTable                                            :505
+  LookUpTableController                                                        :27
+
+State visible after any sweep is the reference's: ``J`` (N,) float64, ``pi`` (N,) int64,
+``J_next``, ``t``, ``k``, ``alpha``, ``cf``, ``grid_sys``, ``sys`` and, if ``save_time_history``,
+``J_list / pi_list / t_list``.  J / pi live on the device; the attributes are fetched lazily.
+
+The sweep itself runs in ``libpyrodp.so`` (CUDA, sm_100a).  There is no CPU path here.
+"""
+import time
+
+import numpy as np
+
+from . import _lib, problem as _problem
+from .engine import Engine
+
+# above this many nodes the per-sweep J/pi history (one full array each per sweep,
+# dynamicprogramming.py:255-258) defaults to off — 13 GB/sweep at 201^4
+HISTORY_MAX_NODES = 1 << 22
+
+
+class LookUpTableController:
+    """pi -> u(x) by n-linear interpolation of the per-axis input tables (dynamicprogramming.py:27-107)."""
+
+    def __init__(self, grid_sys, pi, u_tables=None):
+        if grid_sys.nodes_n != pi.size:
+            raise ValueError("Grid size does not match optimal action table size")
+        self.k, self.m, self.p = 1, grid_sys.sys.m, grid_sys.sys.n
+        self.grid_sys, self.pi = grid_sys, pi
+        self.name = "Tabular Controller"
+        self.rbar = np.zeros(self.k)
+        self.interpol_method = ["linear"] * self.m
+        self._u_tables = u_tables
+        self.compute_interpol_functions()
+
+    def compute_interpol_functions(self):
+        self.u_interpol = []
+        for k in range(self.m):
+            u_k = self._u_tables[k] if self._u_tables is not None else self.grid_sys.get_input_from_policy(self.pi, k)
+            self.u_interpol.append(self.grid_sys.compute_interpolation_function(
+                u_k, self.interpol_method[k], bounds_error=False, fill_value=0))
+
+    def lookup_table_selection(self, x):
+        u = np.zeros(self.m)
+        for k in range(self.m):
+            u[k] = self.u_interpol[k](x)[0]
+        return u
+
+    def c(self, y, r, t=0):
+        return self.lookup_table_selection(y)
+
+
+class DynamicProgramming:
+    """Dynamic programming on a grid sys — Bellman sweeps on the GPU."""
+
+    def __init__(self, grid_sys, cost_function, final_time=0, engine_factory=None):
+        self.grid_sys = grid_sys
+        self.sys = grid_sys.sys
+        self.cf = cost_function
+        self.tf = final_time
+        self.alpha = 1.0
+        self.interpol_method = "linear"
+        self.save_time_history = grid_sys.nodes_n <= HISTORY_MAX_NODES
+        self.max_sweeps = None  # optional guard for solve_bellman_equation (hard part 7)
+        self.verbose = True
+        self.t = self.tf
+        self.k = 0
+        self.start_time = time.time()
+        self._engine_factory = engine_factory
+        self._engine = None
+        self._key = None
+        self._J = self._pi = self._J_next = None
+        self._last_stats = None
+        self.evaluate_terminal_cost()
+        if self.save_time_history:
+            self.t_list, self.J_list, self.pi_list = [self.tf], [self.J], [self.pi]
+
+    # ---- engine management -----------------------------------------------------------------------
+    def _extract(self):
+        return _problem.extract(self.grid_sys, self.cf, self.alpha, self.interpol_method)
+
+    def _make_engine(self, P):
+        if self._engine_factory is not None:
+            return self._engine_factory(self, P)
+        from . import distributed
+        if distributed.is_sharded():
+            return distributed.ShardedEngine(self.grid_sys, self.cf, self.alpha, self.interpol_method)
+        if P.system_id == _lib.PDP_SYS_LUT:
+            return self._make_lut_engine(P)
+        return Engine(P)
+
+    def _make_lut_engine(self, P):
+        eng = Engine(P)
+        x_next, G = build_lookup_tables(self.grid_sys, self.cf, self.tf)
+        eng.set_lut(x_next, G)
+        return eng
+
+    def _ensure_engine(self):
+        """(Re)build the device state if any parameter the sweep reads has changed."""
+        P = self._extract()
+        key = P.fingerprint()
+        if self._engine is None or key != self._key:
+            carry = None
+            if self._engine is not None:
+                carry = self._engine.get_J()
+                self._engine.close()
+            self._engine = self._make_engine(P)
+            self._key = key
+            if carry is not None:
+                self._engine.set_J(carry)
+        return self._engine
+
+    # ---- lazily fetched arrays ----------------------------------------------------------------------
+    @property
+    def J(self):
+        if self._J is None:
+            self._J = self._engine.get_J()
+        return self._J
+
+    @J.setter
+    def J(self, value):
+        self._J = np.array(value, dtype=float)
+        self._ensure_engine().set_J(self._J)
+
+    @property
+    def pi(self):
+        if self._pi is None:
+            self._pi = self._engine.get_pi()
+        return self._pi
+
+    @pi.setter
+    def pi(self, value):
+        self._pi = np.asarray(value)
+
+    @property
+    def J_next(self):
+        if self._J_next is None:
+            self._J_next = self._engine.get_J_next()
+        return self._J_next
+
+    @J_next.setter
+    def J_next(self, value):
+        self._J_next = value
+
+    def _invalidate(self):
+        self._J = self._pi = self._J_next = None
+
+    # ---- reference hooks ---------------------------------------------------------------------------
+    def evaluate_terminal_cost(self):
+        """J = cf.h(x, tf) on every node, pi = 0 (dynamicprogramming.py:159-171), on the device."""
+        eng = self._ensure_engine()
+        if getattr(eng, "lut_mode", False) or eng.problem.system_id == _lib.PDP_SYS_LUT:
+            xs = self.grid_sys.state_from_node_id
+            eng.set_J(np.array([self.cf.h(xs[s, :], self.tf) for s in range(self.grid_sys.nodes_n)], dtype=float))
+        else:
+            eng.eval_terminal_cost()
+        self._invalidate()
+        self._pi = np.zeros(self.grid_sys.nodes_n, dtype=int)
+
+    def initialize_backward_step(self):
+        self.k = self.k + 1
+        self.t = self.t - self.grid_sys.dt
+        self._ensure_engine()
+
+    def compute_backward_step(self):
+        self._last_stats = self._engine.sweep(1)[0]
+        self._invalidate()
+
+    def finalize_backward_step(self):
+        return self._report(self._last_stats, self.k, self.t)
+
+    def _report(self, stats, k, t):
+        elapsed_time = time.time() - self.start_time
+        j_max, delta_max, delta_min = (float(v) for v in stats)
+        if self.verbose:
+            print('%d t:%.2f Elasped:%.2f max: %.2f dmax:%.2f dmin:%.2f' % (k, t, elapsed_time, j_max, delta_max, delta_min))
+        if self.save_time_history:
+            self.J_list.append(self.J)
+            self.t_list.append(t)
+            self.pi_list.append(self.pi)
+        return abs(np.array([delta_max, delta_min])).max()
+
+    # ---- drivers -----------------------------------------------------------------------------------
+    def compute_steps(self, n=50, animate_cost2go=False, animate_policy=False, k=0):
+        if animate_cost2go or animate_policy:
+            raise NotImplementedError("plot/animation helpers are outside the accelerated path")
+        if self.verbose:
+            print('\nComputing %d backward DP iterations:' % n)
+            print('-----------------------------------------')
+        if self.save_time_history:
+            for _ in range(n):
+                self.initialize_backward_step()
+                self.compute_backward_step()
+                self.finalize_backward_step()
+            return
+        # no per-sweep host copies wanted: run all n sweeps back to back on the device
+        eng = self._ensure_engine()
+        stats = eng.sweep(n)
+        self._invalidate()
+        for i in range(n):
+            self.k += 1
+            self.t = self.t - self.grid_sys.dt
+            self._report(stats[i], self.k, self.t)
+        self._last_stats = stats[-1] if n else self._last_stats
+
+    def solve_bellman_equation(self, tol=0.1, animate_cost2go=False, animate_policy=False, k=0):
+        if animate_cost2go or animate_policy:
+            raise NotImplementedError("plot/animation helpers are outside the accelerated path")
+        if self.verbose:
+            print('\nComputing backward DP iterations until dJ<%2.2f:' % tol)
+            print('---------------------------------------------------------')
+        delta = self.cf.INF
+        sweeps = 0
+        while delta > tol:
+            if self.max_sweeps is not None and sweeps >= self.max_sweeps:
+                if self.verbose:
+                    print('\nmax_sweeps reached before dJ<tol')
+                return
+            self.initialize_backward_step()
+            self.compute_backward_step()
+            delta = self.finalize_backward_step()
+            sweeps += 1
+        if self.verbose:
+            print('\nBellman equation solved!')
+
+    # ---- data tools ----------------------------------------------------------------------------------
+    def clean_infeasible_set(self, tol=1):
+        default_action = self.grid_sys.get_nearest_action_id_from_input(self.sys.ubar)
+        self._engine.clean_infeasible_set(tol, int(default_action))
+        self._J = self._pi = None
+
+    def get_lookup_table_controller(self):
+        u_tables = [self._engine.get_input_from_policy(k) for k in range(self.sys.m)]
+        return LookUpTableController(self.grid_sys, self.pi, u_tables)
+
+    def save_latest(self, name='test_data'):
+        np.save(name + '_J_inf', self.J_next)
+        np.save(name + '_pi_inf', self.pi.astype(int))
+
+    def load_J_next(self, name='test_data'):
+        try:
+            self.J_next = np.load(name + '_J_inf' + '.npy')
+        except Exception:
+            print('Failed to load J_next ')
+
+    def plot_cost2go(self, *a, **k):
+        raise NotImplementedError("plotting is outside the accelerated path; use the reference's helpers on dp.J")
+
+    plot_policy = plot_cost2go_3D = animate_cost2go = animate_policy = plot_cost2go
+
+
+class DynamicProgrammingWithLookUpTable(DynamicProgramming):
+    """Name kept for drop-in use: every reference example instantiates this class
+    (dynamicprogramming.py:505).  Known systems run the fused on-the-fly kernel (no tables are
+    ever materialised); anything else runs the LUT-mode kernel on the reference-style tables."""
+
+
+def build_lookup_tables(grid_sys, cf, t=0):
+    """Reference-style dense tables for LUT mode: x_next (N,A,n), G (N,A) with INF folded in
+    (discretizer.py:342-376, dynamicprogramming.py:517-553).  Uses the grid's own tables when
+    it has them (a real pyro GridDynamicSystem built with lookup=True), else calls sys.f."""
+    sys = grid_sys.sys
+    N, A, n = grid_sys.nodes_n, grid_sys.actions_n, sys.n
+    X, U = grid_sys.state_from_node_id, grid_sys.input_from_action_id
+    have = all(hasattr(grid_sys, a) for a in ("x_next_table", "x_next_isok", "action_isok"))
+    if have:
+        x_next, x_ok, a_ok = grid_sys.x_next_table, grid_sys.x_next_isok, grid_sys.action_isok
+    else:
+        x_next = np.zeros((N, A, n))
+        x_ok = np.zeros((N, A), dtype=bool)
+        a_ok = np.zeros((N, A), dtype=bool)
+        for s in range(N):
+            for a in range(A):
+                xn = sys.f(X[s, :], U[a, :]) * grid_sys.dt + X[s, :]
+                x_next[s, a, :] = xn
+                x_ok[s, a] = sys.isavalidstate(xn)
+                a_ok[s, a] = sys.isavalidinput(X[s, :], U[a, :])
+    G = np.full((N, A), float(cf.INF))
+    for s in range(N):
+        for a in range(A):
+            if a_ok[s, a] and x_ok[s, a]:
+                G[s, a] = cf.g(X[s, :], U[a, :], t) * grid_sys.dt
+    return x_next, G
