@@ -1,0 +1,80 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (tier-0) in this container.
+
+    PYTHONPATH=. python oracle/gen_golden.py            # needs /root/reference (or $PYRO_REF)
+
+The reference ships no tests or golden vectors for this path, so these
+fixtures — outputs of the reference's own DynamicProgrammingWithLookUpTable
+(pyro/planning/dynamicprogramming.py:505-570) on small grids of the four BASELINE systems —
+are the pin for the oracle and for the CUDA path.  Each file holds the case definition (JSON),
+J and pi snapshots after the listed sweep counts, and a strided sample of the reference's
+x_next_table / G tables (discretizer.py:349, dynamicprogramming.py:523).
+The same case definitions are replayed by tests/cases.py on the mirrors of pyro_b200.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_loader  # noqa: E402
+from tests.cases import CASES  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def build_reference(ns, case):
+    cls = {"SinglePendulum": ns.pendulum.SinglePendulum, "DoublePendulum": ns.pendulum.DoublePendulum,
+           "TwoLinkManipulator": ns.manipulator.TwoLinkManipulator, "CartPole": ns.cartpole.CartPole}[case["system"]]
+    sys_ = cls()
+    for key in ("x_lb", "x_ub", "u_lb", "u_ub"):
+        if key in case:
+            getattr(sys_, key)[:] = case[key]
+    for key, val in case.get("sys_params", {}).items():
+        setattr(sys_, key, val)
+    grid = ns.discretizer.GridDynamicSystem(sys_, case["x_grid_dim"], case["u_grid_dim"], case.get("dt", 0.05))
+    if case.get("cost", "quadratic") == "quadratic":
+        cf = ns.costfunction.QuadraticCostFunction.from_sys(sys_)
+        for key in ("Q", "R", "S"):
+            if key in case:
+                setattr(cf, key, np.diag(np.array(case[key], float)) if np.ndim(case[key]) == 1 else np.array(case[key], float))
+    else:
+        cf = ns.costfunction.TimeCostFunction(np.array(case["xbar"], float))
+    if "xbar" in case:
+        cf.xbar = np.array(case["xbar"], float)
+    for key in ("INF", "EPS"):
+        if key in case:
+            setattr(cf, key, case[key])
+    dp = ns.dynamicprogramming.DynamicProgrammingWithLookUpTable(grid, cf)
+    dp.alpha = case.get("alpha", 1.0)
+    return sys_, grid, cf, dp
+
+
+def main():
+    ns = ref_loader.load()
+    os.makedirs(OUT, exist_ok=True)
+    for name, case in CASES.items():
+        with ref_loader.quiet():
+            sys_, grid, cf, dp = build_reference(ns, case)
+            out = {"case": json.dumps(case), "J0": dp.J.copy()}
+            stride = case.get("table_stride", 1)
+            out["table_stride"] = stride
+            out["x_next_sample"] = grid.x_next_table[::stride].copy()
+            out["x_next_isok_sample"] = grid.x_next_isok[::stride].copy()
+            out["action_isok_sample"] = grid.action_isok[::stride].copy()
+            out["G_sample"] = dp.G[::stride].copy()
+            k = 0
+            for target in case["snapshots"]:
+                dp.compute_steps(target - k)
+                k = target
+                out[f"J_{k}"] = dp.J.copy()
+                out[f"pi_{k}"] = dp.pi.astype(np.int64)
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(f"{name}: N={grid.nodes_n} A={grid.actions_n} snapshots={case['snapshots']} "
+              f"J_max={dp.J.max():.6f} -> {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,82 @@
+"""Parity cases shared by the golden generator (reference side) and the tests (our side).
+
+Each case is plain data.  ``build_case`` instantiates it on the pyro_b200 mirrors exactly the
+way oracle/gen_golden.py instantiates it on the real reference classes.
+"""
+import numpy as np
+
+PI = float(np.pi)
+
+CASES = {
+    # BASELINE config 1: SinglePendulum 51x51, 11 actions (dynamicprogramming.py:774-783 settings)
+    "pend_51x51x11": dict(system="SinglePendulum", x_grid_dim=[51, 51], u_grid_dim=[11], xbar=[-3.14, 0.0], INF=300.0,
+                          snapshots=[1, 2, 10, 50, 100]),
+    "pend_101x101x21": dict(system="SinglePendulum", x_grid_dim=[101, 101], u_grid_dim=[21], xbar=[-3.14, 0.0], INF=300.0,
+                            snapshots=[1, 10, 50], table_stride=7),
+    # non-square grid, discount, damping, custom bounds, minimum-time cost with a real target zone
+    "pend_time_41x61x7": dict(system="SinglePendulum", x_grid_dim=[41, 61], u_grid_dim=[7], cost="time", xbar=[-3.14, 0.0],
+                              INF=50.0, EPS=0.5, alpha=0.9, dt=0.1, sys_params={"d1": 0.3},
+                              x_lb=[-4.0, -5.0], x_ub=[1.0, 6.0], u_lb=[-8.0], u_ub=[8.0], snapshots=[1, 5, 20]),
+    # the reference's only 4-D example (examples/demos_by_tool/dynamicprogramming/double_pendulum_optimal_swingup.py:19-54)
+    "dpend_example": dict(system="DoublePendulum", x_grid_dim=[11, 9, 13, 11], u_grid_dim=[3, 5], dt=0.1,
+                          x_lb=[-5.0, -1.5, -4.0, -4.0], x_ub=[0.5, 4.0, 5.5, 7.0], u_lb=[-12.0, -12.0], u_ub=[12.0, 12.0],
+                          xbar=[0.0, 0.0, 0.0, 0.0], Q=[1.0, 0.5, 0.1, 0.05], R=[0.05, 0.05], INF=1000.0, EPS=1.0,
+                          snapshots=[1, 2, 10, 30], table_stride=5),
+    "dpend_default_11": dict(system="DoublePendulum", x_grid_dim=[11, 11, 11, 11], u_grid_dim=[3, 3], INF=1000.0,
+                             snapshots=[1, 2, 10], table_stride=5),
+    "twolink_9": dict(system="TwoLinkManipulator", x_grid_dim=[9, 9, 9, 9], u_grid_dim=[3, 3], INF=1000.0,
+                      snapshots=[1, 2, 10], table_stride=3),
+    # small torques so most transitions stay in bounds and the interpolation is exercised
+    "twolink_soft": dict(system="TwoLinkManipulator", x_grid_dim=[9, 11, 9, 13], u_grid_dim=[5, 3], INF=500.0, alpha=0.95,
+                         u_lb=[-0.3, -0.05], u_ub=[0.3, 0.05], snapshots=[1, 2, 10], table_stride=3),
+    "cartpole_swingup": dict(system="CartPole", x_grid_dim=[9, 11, 9, 11], u_grid_dim=[5], xbar=[0.0, PI, 0.0, 0.0],
+                             INF=1000.0, snapshots=[1, 2, 10, 30], table_stride=3),
+}
+
+
+def build_case(case, lookup=False):
+    """Instantiate a case on the pyro_b200 mirrors -> (sys, grid_sys, cf)."""
+    from pyro_b200 import costfunction, discretizer, systems
+    sys_ = systems.SYSTEMS[case["system"]]()
+    for key in ("x_lb", "x_ub", "u_lb", "u_ub"):
+        if key in case:
+            getattr(sys_, key)[:] = case[key]
+    for key, val in case.get("sys_params", {}).items():
+        setattr(sys_, key, val)
+    grid = discretizer.GridDynamicSystem(sys_, case["x_grid_dim"], case["u_grid_dim"], case.get("dt", 0.05), lookup=lookup)
+    if case.get("cost", "quadratic") == "quadratic":
+        cf = costfunction.QuadraticCostFunction.from_sys(sys_)
+        for key in ("Q", "R", "S"):
+            if key in case:
+                setattr(cf, key, np.diag(np.array(case[key], float)) if np.ndim(case[key]) == 1 else np.array(case[key], float))
+    else:
+        cf = costfunction.TimeCostFunction(np.array(case["xbar"], float))
+    if "xbar" in case:
+        cf.xbar = np.array(case["xbar"], float)
+    for key in ("INF", "EPS"):
+        if key in case:
+            setattr(cf, key, case[key])
+    return sys_, grid, cf
+
+
+def oracle_objects(case):
+    """The same case on the independent NumPy oracle -> (GridOracle, cost)."""
+    from oracle import np_oracle as npo
+    spec = npo.SysSpec(case["system"], **case.get("sys_params", {}))
+    for key in ("x_lb", "x_ub", "u_lb", "u_ub"):
+        if key in case:
+            setattr(spec, key, np.array(case[key], float))
+    grid = npo.GridOracle(spec, case["x_grid_dim"], case["u_grid_dim"], case.get("dt", 0.05))
+    if case.get("cost", "quadratic") == "quadratic":
+        cost = npo.QuadCost(spec.n, spec.m)
+        for key in ("Q", "R", "S"):
+            if key in case:
+                setattr(cost, key, np.diag(np.array(case[key], float)) if np.ndim(case[key]) == 1 else np.array(case[key], float))
+    else:
+        cost = npo.TimeCost(case["xbar"])
+    if "xbar" in case:
+        cost.xbar = np.array(case["xbar"], float)
+    for key in ("INF", "EPS"):
+        if key in case:
+            setattr(cost, key, case[key])
+    return grid, cost

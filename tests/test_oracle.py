@@ -1,0 +1,121 @@
+"""The oracle against the reference: golden fixtures (tier-0 outputs) and, when importable, live runs."""
+import itertools
+import json
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle, np_oracle as npo, ref_loader
+from pyro_b200 import problem
+from tests.cases import CASES, build_case, oracle_objects
+from tests.conftest import load_golden
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_numpy_oracle_matches_reference_goldens(name):
+    """Tier-1 NumPy restatement == reference: tables, then J / pi after every recorded sweep count."""
+    case, gold = CASES[name], load_golden(name)
+    assert json.loads(str(gold["case"])) == json.loads(json.dumps(case)), "golden file is stale; rerun oracle/gen_golden.py"
+    grid, cost = oracle_objects(case)
+    stride = int(gold["table_stride"])
+    # tables (discretizer.py:342-376, dynamicprogramming.py:517-553) on the sampled nodes
+    x_next, x_ok, a_ok, G = grid.tables(cost)
+    assert np.array_equal(x_next[::stride], gold["x_next_sample"])
+    assert np.array_equal(x_ok[::stride], gold["x_next_isok_sample"])
+    assert np.array_equal(a_ok[::stride], gold["action_isok_sample"])
+    assert np.array_equal(G[::stride], gold["G_sample"])
+    # sweeps
+    J = grid.terminal(cost)
+    assert np.array_equal(J, gold["J0"])
+    k = 0
+    alpha = case.get("alpha", 1.0)
+    for target in case["snapshots"]:
+        for _ in range(target - k):
+            J, pi = grid.sweep(J, cost, alpha)
+        k = target
+        assert np.array_equal(J, gold[f"J_{k}"]), f"J differs after {k} sweeps"
+        assert np.array_equal(pi, gold[f"pi_{k}"]), f"pi differs after {k} sweeps"
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_c_oracle_matches_reference_goldens(name):
+    """Plain-C restatement (fed by the product's descriptor) == reference, bit for bit."""
+    case, gold = CASES[name], load_golden(name)
+    _, grid, cf = build_case(case)
+    P = problem.extract(grid, cf, case.get("alpha", 1.0))
+    J = c_oracle.terminal(P)
+    assert np.array_equal(J, gold["J0"])
+    k = 0
+    for target in case["snapshots"]:
+        for _ in range(target - k):
+            J, pi = c_oracle.sweep_fused(P, J)
+        k = target
+        assert np.array_equal(J, gold[f"J_{k}"])
+        assert np.array_equal(pi, gold[f"pi_{k}"])
+
+
+def test_c_lut_sweep_matches_goldens():
+    case, gold = CASES["pend_51x51x11"], load_golden("pend_51x51x11")
+    _, grid, cf = build_case(case)
+    P = problem.extract(grid, cf, 1.0)
+    J, pi = c_oracle.sweep_lut(P, gold["J0"], gold["x_next_sample"], gold["G_sample"])
+    assert np.array_equal(J, gold["J_1"]) and np.array_equal(pi, gold["pi_1"])
+
+
+@pytest.mark.parametrize("n", [2, 3, 4])
+def test_rgi_restatement_matches_scipy(n):
+    """rgi_linear == scipy RegularGridInterpolator(linear, bounds_error=False, fill_value=0), bitwise,
+    on random points, exact level hits, both bounds, and just-outside points."""
+    from scipy.interpolate import RegularGridInterpolator
+    rng = np.random.default_rng(n)
+    dims = [7, 5, 6, 4][:n]
+    levels = [np.linspace(-1.0 - d, 2.0 + 0.5 * d, dims[d]) for d in range(n)]
+    values = rng.uniform(0, 300, dims)
+    pts = [rng.uniform(-1.2, 1.2, (4000, n)) * np.array([lv[-1] - lv[0] for lv in levels]) / 2
+           + np.array([(lv[-1] + lv[0]) / 2 for lv in levels])]
+    special = [np.concatenate([lv, [np.nextafter(lv[0], -np.inf), np.nextafter(lv[-1], np.inf),
+                                    np.nextafter(lv[0], np.inf), np.nextafter(lv[-1], -np.inf)]]) for lv in levels]
+    pts.append(np.array(list(itertools.islice(itertools.product(*special), 0, 20000))))
+    xi = np.concatenate(pts)
+    want = RegularGridInterpolator(tuple(levels), values, "linear", False, 0)(xi)
+    got = npo.rgi_linear(levels, values, xi)
+    assert np.array_equal(got, want)
+
+
+def test_scipy_and_own_rgi_give_identical_sweeps():
+    grid, cost = oracle_objects(CASES["dpend_example"])
+    J0 = np.random.default_rng(0).uniform(0, 300, grid.N)
+    a = grid.sweep(J0, cost, 1.0, use_scipy=False)
+    b = grid.sweep(J0, cost, 1.0, use_scipy=True)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_survey_anchor_values():
+    """Sanity anchors measured on the reference during the survey."""
+    gold = load_golden("pend_51x51x11")
+    grid, cost = oracle_objects(CASES["pend_51x51x11"])
+    J = grid.terminal(cost)
+    for _ in range(5):
+        J, _ = grid.sweep(J, cost)
+    assert abs(J.max() - 319.38) < 0.01
+    x_next, x_ok, a_ok, _ = grid.tables(cost)
+    assert a_ok.all()
+    assert abs((~x_ok).mean() - 0.0461) < 1e-3
+    assert gold["J_100"].shape == (2601,)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference not present (GPU box)")
+def test_live_reference_base_class_equals_oracle():
+    """The literal per-pair formulation (dynamicprogramming.py:195-236) run live == the oracle."""
+    ns = ref_loader.load()
+    case = dict(system="SinglePendulum", x_grid_dim=[15, 13], u_grid_dim=[5], xbar=[-3.14, 0.0], INF=300.0)
+    with ref_loader.quiet():
+        s = ns.pendulum.SinglePendulum()
+        g = ns.discretizer.GridDynamicSystem(s, case["x_grid_dim"], case["u_grid_dim"], lookup=False)
+        cf = ns.costfunction.QuadraticCostFunction.from_sys(s)
+        cf.xbar, cf.INF = np.array(case["xbar"]), case["INF"]
+        dp = ns.dynamicprogramming.DynamicProgramming(g, cf)
+        dp.compute_steps(3)
+    grid, cost = oracle_objects(case)
+    J, pi, _ = grid.run(cost, 3)
+    assert np.array_equal(J, dp.J) and np.array_equal(pi, dp.pi)

@@ -1,0 +1,242 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the reference goldens and the oracle.
+
+Bars (BASELINE.json north_star): J within 1e-5 relative (L-inf over max|J_ref|), pi index-exact.
+The kernels restate the reference's IEEE operations one by one, so the tests additionally record
+whether J is bit-identical (it is expected to be when the box's NumPy produces the same table
+bits as the container that generated the goldens).
+"""
+import numpy as np
+import pytest
+
+from oracle import c_oracle, np_oracle as npo
+from pyro_b200 import _lib, dynamicprogramming, problem
+from pyro_b200.engine import Engine
+from tests.cases import CASES, build_case, oracle_objects
+from tests.conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5  # north_star tolerance on J
+
+
+def rel_err(J, J_ref):
+    return np.abs(J - J_ref).max() / np.abs(J_ref).max()
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_fused_kernels_match_reference_goldens(name):
+    """Public API (DynamicProgramming.compute_steps) vs tier-0 fixtures at every snapshot."""
+    case, gold = CASES[name], load_golden(name)
+    _, grid, cf = build_case(case)
+    dp = dynamicprogramming.DynamicProgrammingWithLookUpTable(grid, cf)
+    dp.alpha, dp.verbose = case.get("alpha", 1.0), False
+    assert rel_err(dp.J, gold["J0"]) == 0 or np.array_equal(dp.J, gold["J0"])
+    k = 0
+    for target in case["snapshots"]:
+        dp.compute_steps(target - k)
+        k = target
+        J_ref, pi_ref = gold[f"J_{k}"], gold[f"pi_{k}"]
+        assert dp.J.dtype == np.float64 and dp.pi.dtype == np.int64 and dp.J.shape == (grid.nodes_n,)
+        err, mism = rel_err(dp.J, J_ref), int((dp.pi != pi_ref).sum())
+        print(f"{name} k={k}: rel err {err:.2e}, pi mismatches {mism}, bit-exact {np.array_equal(dp.J, J_ref)}")
+        assert err <= RTOL and mism == 0
+    assert dp._engine.launch_count >= case["snapshots"][-1]
+
+
+@pytest.mark.parametrize("name", ["pend_51x51x11", "dpend_example", "cartpole_swingup"])
+def test_lut_mode_kernel_is_bit_exact(name):
+    """LUT-mode kernel (generic fallback, dynamicprogramming.py:557-570) on reference-identical tables: exact."""
+    case, gold = CASES[name], load_golden(name)
+    _, grid, cf = build_case(case)
+    ogrid, ocost = oracle_objects(case)
+    x_next, _, _, G = ogrid.tables(ocost)  # bit-identical to the reference's tables (tests/test_oracle.py)
+    eng = Engine(problem.extract(grid, cf, case.get("alpha", 1.0), force_lut=True))
+    eng.set_lut(x_next, G)
+    eng.set_J(gold["J0"])
+    k = 0
+    for target in case["snapshots"][:3]:
+        stats = eng.sweep(target - k)
+        k = target
+        assert np.array_equal(eng.get_J(), gold[f"J_{k}"]) and np.array_equal(eng.get_pi(), gold[f"pi_{k}"])
+    d = gold[f"J_{k}"] - eng.get_J_next()
+    assert stats[-1, 0] == gold[f"J_{k}"].max() and stats[-1, 1] == d.max() and stats[-1, 2] == d.min()
+    eng.close()
+
+
+def test_lut_mode_3d_generic_system():
+    """n = 3 has no fused kernel: a synthetic 3-state system through LUT mode vs the NumPy RGI restatement."""
+    rng = np.random.default_rng(3)
+    dims, A = (9, 7, 8), 6
+    levels = [np.linspace(-1, 1, dims[0]), np.linspace(0, 3, dims[1]), np.linspace(-2, 5, dims[2])]
+    N = int(np.prod(dims))
+    X = np.stack([g.reshape(-1) for g in np.meshgrid(*levels, indexing="ij")], axis=1)
+    x_next = X[:, None, :] + rng.normal(0, 0.4, (N, A, 3))
+    x_next[::17, 0, :] = X[::17]  # exact node hits
+    x_next[5::19, 1, 2] = 5.0     # exactly on the upper bound
+    oob = np.any((x_next < [-1, 0, -2]) | (x_next > [1, 3, 5]), axis=-1)
+    G = np.where(oob, 77.0, rng.uniform(0, 1, (N, A)))
+    J0 = rng.uniform(0, 50, N)
+
+    class Sys3:
+        n, m = 3, 1
+        x_lb, x_ub = np.array([-1.0, 0.0, -2.0]), np.array([1.0, 3.0, 5.0])
+        u_lb, u_ub = np.array([-1.0]), np.array([1.0])
+
+    class Grid3:
+        sys, dt = Sys3(), 0.05
+        x_grid_dim, u_grid_dim = np.array(dims), np.array([A])
+        x_level, u_level = levels, [np.linspace(-1, 1, A)]
+
+    class Cost3:
+        INF = 77.0
+    eng = Engine(problem.extract(Grid3(), Cost3(), 0.97))
+    assert eng.problem.system_id == _lib.PDP_SYS_LUT
+    eng.set_lut(x_next, G)
+    eng.set_J(J0)
+    eng.sweep(1)
+    J_ref, pi_ref = npo.lut_sweep(levels, dims, J0, x_next, G, 0.97, use_scipy=True)
+    assert np.array_equal(eng.get_J(), J_ref) and np.array_equal(eng.get_pi(), pi_ref)
+    eng.close()
+
+
+MID = {
+    "pend_301": dict(system="SinglePendulum", x_grid_dim=[301, 257], u_grid_dim=[41], xbar=[-3.14, 0.0], INF=300.0),
+    "dpend_21": dict(CASES["dpend_example"], x_grid_dim=[21, 19, 23, 21], u_grid_dim=[7, 5]),
+    "twolink_21": dict(CASES["twolink_soft"], x_grid_dim=[21, 17, 21, 25], u_grid_dim=[5, 7]),
+    "cartpole_25": dict(CASES["cartpole_swingup"], x_grid_dim=[15, 25, 21, 27], u_grid_dim=[11]),
+}
+
+
+@pytest.mark.parametrize("name", list(MID))
+def test_mid_size_random_J_equals_c_oracle(name):
+    """Sizes the reference cannot build in reasonable time; rough (random) J so every corner weight matters."""
+    case = MID[name]
+    _, grid, cf = build_case(case)
+    P = problem.extract(grid, cf, case.get("alpha", 1.0))
+    eng = Engine(P)
+    J0 = np.random.default_rng(0).uniform(0, 300, P.N)
+    eng.set_J(J0)
+    stats = eng.sweep(2)
+    J1, pi1 = c_oracle.sweep_fused(P, J0)
+    J2, pi2 = c_oracle.sweep_fused(P, J1)
+    J, pi = eng.get_J(), eng.get_pi()
+    print(f"{name}: rel err {rel_err(J, J2):.2e}, pi mismatches {(pi != pi2).sum()}, bit-exact {np.array_equal(J, J2)}")
+    assert np.array_equal(J, J2) and np.array_equal(pi, pi2)
+    assert np.array_equal(eng.get_J_next(), J1)
+    d = J2 - J1
+    assert stats[1, 0] == J2.max() and stats[1, 1] == d.max() and stats[1, 2] == d.min()
+    eng.close()
+
+
+def test_full_size_config2_sampled_against_oracle_and_properties():
+    """BASELINE config 2 (SinglePendulum 1001x1001x201) at full size: random node ranges against the C
+    oracle, plus size-independent properties (determinism, monotonicity of the Bellman operator,
+    constant-shift equivariance for alpha = 1 on nodes whose minimiser is a valid transition)."""
+    case = dict(system="SinglePendulum", x_grid_dim=[1001, 1001], u_grid_dim=[201], xbar=[-3.14, 0.0], INF=300.0)
+    _, grid, cf = build_case(case)
+    P = problem.extract(grid, cf, 1.0)
+    eng = Engine(P)
+    rng = np.random.default_rng(1)
+    J0 = rng.uniform(0, 250, P.N)
+    eng.set_J(J0)
+    eng.sweep(1)
+    J1, pi1 = eng.get_J(), eng.get_pi()
+    for lo in list(rng.integers(0, P.N - 512, 24)) + [0, P.N - 512, 1001 * 500]:
+        Jr, pr = c_oracle.sweep_fused(P, J0, int(lo), int(lo) + 512)
+        assert np.array_equal(J1[lo:lo + 512], Jr) and np.array_equal(pi1[lo:lo + 512], pr)
+    # determinism
+    eng.set_J(J0)
+    eng.sweep(1)
+    assert np.array_equal(eng.get_J(), J1) and np.array_equal(eng.get_pi(), pi1)
+    # monotone: J0 <= J0' => T(J0) <= T(J0')
+    eng.set_J(J0 + rng.uniform(0, 5, P.N))
+    eng.sweep(1)
+    assert (eng.get_J() >= J1 - 1e-9).all()
+    # shift: T(J0 + c) = T(J0) + c where the minimiser is not the INF branch
+    eng.set_J(J0 + 10.0)
+    eng.sweep(1)
+    Js = eng.get_J()
+    finite = (J1 < 299.0) & (Js < 299.0)
+    assert finite.mean() > 0.5 and np.abs(Js[finite] - J1[finite] - 10.0).max() < 1e-9
+    eng.close()
+
+
+def test_edge_cases():
+    # smallest legal grid (2 levels per axis), a single action, and a grid where every transition leaves the box
+    tiny = dict(system="SinglePendulum", x_grid_dim=[2, 2], u_grid_dim=[1], u_lb=[0.0], u_ub=[0.0], INF=9.0)
+    _, grid, cf = build_case(tiny)
+    P = problem.extract(grid, cf, 1.0)
+    eng = Engine(P)
+    eng.eval_terminal_cost()
+    eng.sweep(3)
+    Jr, pr, _ = c_oracle.run(P, 3)
+    assert np.array_equal(eng.get_J(), Jr) and np.array_equal(eng.get_pi(), pr) and (pr == 0).all()
+    eng.close()
+    allout = dict(system="DoublePendulum", x_grid_dim=[3, 3, 3, 3], u_grid_dim=[2, 2], dt=50.0, INF=123.0,
+                  x_lb=[-1, -1, 1, 1], x_ub=[1, 1, 2, 2])
+    _, grid, cf = build_case(allout)
+    P = problem.extract(grid, cf, 1.0)
+    eng = Engine(P)
+    eng.eval_terminal_cost()
+    st = eng.sweep(1)
+    assert (eng.get_J() == 123.0).all() and (eng.get_pi() == 0).all() and st[0, 0] == 123.0
+    eng.close()
+
+
+def test_terminal_cost_kernel_and_policy_tools():
+    case = dict(CASES["dpend_example"], S=[2.0, 0.3, 0.0, 1.5])
+    _, grid, cf = build_case(case)
+    P = problem.extract(grid, cf, 1.0)
+    eng = Engine(P)
+    eng.eval_terminal_cost()
+    ogrid, ocost = oracle_objects(case)
+    assert np.array_equal(eng.get_J(), ogrid.terminal(ocost))
+    assert np.array_equal(eng.get_J(), c_oracle.terminal(P))
+    eng.sweep(4)
+    pi = eng.get_pi()
+    for k in range(2):
+        assert np.array_equal(eng.get_input_from_policy(k), grid.get_input_from_policy(pi, k))
+    J = eng.get_J()
+    eng.clean_infeasible_set(1.0, 7)
+    bad = J > cf.INF - 1.0
+    J2, pi2 = eng.get_J(), eng.get_pi()
+    assert bad.any() and (J2[bad] == cf.INF).all() and (pi2[bad] == 7).all()
+    assert np.array_equal(J2[~bad], J[~bad]) and np.array_equal(pi2[~bad], pi[~bad])
+    eng.close()
+
+
+def test_abi_error_behaviour():
+    _, grid, cf = build_case(CASES["pend_51x51x11"])
+    eng = Engine(problem.extract(grid, cf, 1.0))
+    with pytest.raises(RuntimeError, match="no cost-to-go"):
+        eng.sweep(1)
+    with pytest.raises(ValueError, match="Grid size does not match"):
+        eng.set_J(np.zeros(5))
+    with pytest.raises(RuntimeError):
+        eng.set_lut(np.zeros(2601 * 11 * 2), np.zeros(2601 * 11))  # not a LUT handle
+    eng.eval_terminal_cost()
+    with pytest.raises(ValueError):
+        eng.get_input_from_policy(3)
+    eng.close()
+    P = problem.extract(grid, cf, 1.0)
+    P.c.dims[1] = 1
+    with pytest.raises(ValueError):
+        Engine(P)
+
+
+def test_exact_div_equals_ieee_division():
+    """The 3-instruction corrected quotient used for the normalised distance == IEEE division."""
+    import ctypes as C
+    lib = C.CDLL(_lib.LIB_PATH)
+    rng = np.random.default_rng(5)
+    n = 1 << 20
+    den = np.concatenate([np.diff(np.linspace(-2 * np.pi, 2 * np.pi, 1001)).repeat(400)[: n // 2],
+                          rng.uniform(1e-3, 10.0, n - n // 2)])
+    a = den * rng.uniform(0, 1, n)
+    a[:1000] = den[:1000]
+    a[1000:2000] = 0.0
+    qf, qi = np.empty(n), np.empty(n)
+    rc = lib.pdp_test_exact_div(C.c_void_p(a.ctypes.data), C.c_void_p(den.ctypes.data), C.c_void_p(qf.ctypes.data),
+                                C.c_void_p(qi.ctypes.data), C.c_int64(n))
+    assert rc == 0
+    assert np.array_equal(qi, a / den)
+    assert np.array_equal(qf, qi)
