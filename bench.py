@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py — Bellman-sweep throughput of the B200 grid-DP engine (state-action evals/s).
+
+    python bench.py --gpus 1 --steps 20 --warmup 3            # own arm (CUDA kernels)
+    python bench.py --impl reference --steps 3 --warmup 1     # reference arm (CPU, oracle port)
+    torchrun ... bench.py --gpus N ...                        # N>1: one rank per GPU, NCCL
+
+A "step" is ONE Bellman sweep (one pass of the hot path over the whole grid): for every node
+and every action, Euler step, n-linear interpolation of J, stage cost, min/argmin, plus the
+fused convergence reduction (and, for N>1, the all-gather of the new J over NVLink).
+Metric, config and roofline definitions: BASELINE.json / SURVEY.md section 8(d) / DESIGN.md.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PI = float(np.pi)
+# BASELINE.json configs (SURVEY.md 8d "Concrete synthetic inputs")
+WORKLOADS = {
+    "cfg1": dict(system="SinglePendulum", x_grid_dim=[51, 51], u_grid_dim=[11], xbar=[-3.14, 0.0], INF=300.0, dt=0.05),
+    "cfg2": dict(system="SinglePendulum", x_grid_dim=[1001, 1001], u_grid_dim=[201], xbar=[-3.14, 0.0], INF=300.0, dt=0.05),
+    "cfg3": dict(system="TwoLinkManipulator", x_grid_dim=[101] * 4, u_grid_dim=[21, 21], INF=1000.0, dt=0.05),
+    "cfg4": dict(system="CartPole", x_grid_dim=[151] * 4, u_grid_dim=[51], xbar=[0.0, PI, 0.0, 0.0], INF=1000.0, dt=0.05),
+    "cfg5": dict(system="DoublePendulum", x_grid_dim=[201] * 4, u_grid_dim=[31, 31], dt=0.1,
+                 x_lb=[-5.0, -1.5, -4.0, -4.0], x_ub=[0.5, 4.0, 5.5, 7.0], u_lb=[-12.0, -12.0], u_ub=[12.0, 12.0],
+                 xbar=[0.0, 0.0, 0.0, 0.0], Q=[1.0, 0.5, 0.1, 0.05], R=[0.05, 0.05], INF=1000.0, EPS=1.0),
+}
+L2_FLUSH_BYTES = 256 << 20  # > 126 MB L2
+
+
+def b_eval(n, A):
+    """Algorithmic bytes per eval, the contract figure of SURVEY.md 8(d): 8*2^n + 24/A."""
+    return 8.0 * (1 << n) + 24.0 / A
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(workload):
+    """dram bytes per launch of the sweep kernel from the committed ncu capture, or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(workload)
+        except Exception:
+            return None
+    return None
+
+
+def weak_scaled(case, world):
+    """Per-GPU work fixed: axis 0 carries world x the planes of the named configuration."""
+    case = dict(case)
+    dims = list(case["x_grid_dim"])
+    dims[0] = dims[0] * world
+    case["x_grid_dim"] = dims
+    return case
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if sm:
+            busy = [s for s in sm if s > 0.5 * max(mx)] or sm
+            out.update(sm_mhz=float(np.median(busy)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU baselines (oracle port) — rank 0 only
+# --------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    """One process: the reference's LUT sweep (dynamicprogramming.py:564-570, scipy RGI) on a node range."""
+    case, lo, hi, reps = args
+    from oracle import np_oracle as npo
+    from tests.cases import oracle_objects
+    grid, cost = oracle_objects(case)
+    J_next = np.random.default_rng(0).uniform(0, 250, grid.N)
+    x_next, _, _, G = grid.tables(cost, lo, hi)  # one-off table build, NOT timed (reference builds them once)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        npo.lut_sweep(grid.x_level, grid.dims, J_next, x_next, G, 1.0, use_scipy=True)
+    return time.perf_counter() - t0
+
+
+def cpu_reference_rate(case, n_procs, nodes_per_proc, reps):
+    """evals/s of the NumPy/SciPy LUT sweep port with n_procs processes on a bounded node sample."""
+    import multiprocessing as mp
+    from tests.cases import oracle_objects
+    grid, _ = oracle_objects(case)
+    nodes_per_proc = min(nodes_per_proc, grid.N // n_procs)
+    jobs = [(case, i * nodes_per_proc, (i + 1) * nodes_per_proc, reps) for i in range(n_procs)]
+    t0 = time.perf_counter()
+    if n_procs == 1:
+        times = [_cpu_worker(jobs[0])]
+    else:
+        with mp.get_context("fork").Pool(n_procs) as pool:
+            times = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    evals = n_procs * nodes_per_proc * grid.A * reps
+    return evals / max(times), evals, wall
+
+
+def cpu_native_rate(case, n_nodes, reps):
+    """evals/s of the C/OpenMP restatement (oracle/dp_oracle.c), all host threads, on-the-fly dynamics."""
+    from oracle import c_oracle
+    from pyro_b200 import problem
+    from tests.cases import build_case
+    _, grid, cf = build_case(case)
+    P = problem.extract(grid, cf, 1.0)
+    n_nodes = min(n_nodes, P.N)
+    J_next = np.random.default_rng(0).uniform(0, 250, P.N)
+    c_oracle.sweep_fused(P, J_next, 0, min(4096, n_nodes))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        c_oracle.sweep_fused(P, J_next, 0, n_nodes)
+    dt = time.perf_counter() - t0
+    return n_nodes * P.A * reps / dt, c_oracle.n_threads_default()
+
+
+def host_cores():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def run_reference_arm(args, case, wl_name):
+    """--impl reference: the reference's CPU path (oracle port: NumPy + SciPy RGI LUT sweep) on host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    from tests.cases import oracle_objects
+    grid, _ = oracle_objects(case)
+    n, A = grid.spec.n, grid.A
+    # bounded sample: ~2e6 evals per process per step keeps one step at a fraction of a second
+    nodes_per_proc = max(1, int(2.0e6 // A))
+    for _ in range(max(args.warmup, 0)):
+        cpu_reference_rate(case, cores, nodes_per_proc, 1)
+    t0 = time.perf_counter()
+    rates = []
+    for _ in range(args.steps):
+        r, evals, _ = cpu_reference_rate(case, cores, nodes_per_proc, 1)
+        rates.append(r)
+    wall = time.perf_counter() - t0
+    value = float(np.median(rates))
+    native, native_threads = cpu_native_rate(case, 1 << 15, 2)
+    sample = (f"{cores} processes x {nodes_per_proc} nodes x {A} actions per step of the same grid "
+              f"(tables prebuilt, LUT sweep only, scipy RGI; dynamicprogramming.py:564-570)")
+    line = {
+        "impl": "reference", "metric": "state_action_evals_per_s", "value": value, "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl_name, **{k: case[k] for k in ("system", "x_grid_dim", "u_grid_dim")},
+                   "note": "CPU reference path; each step = a bounded node sample of the workload"},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline_native": {"value": native, "unit": "evals/s", "cores": native_threads, "kind": "port",
+                                "sample": "C/OpenMP restatement (oracle/dp_oracle.c), 32768 nodes x all actions, on-the-fly dynamics"},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "roofline": None,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# own arm
+# --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    base = WORKLOADS[args.workload]
+    case = weak_scaled(base, world) if (args.scaling == "weak" and world > 1) else dict(base)
+    wl_name = {"cfg1": "SinglePendulum 51x51 x 11 actions", "cfg2": "SinglePendulum 1001x1001 state grid x 201 actions",
+               "cfg3": "TwoLinkManipulator 101^4 x 21^2 actions", "cfg4": "CartPole 151^4 x 51 actions",
+               "cfg5": "DoublePendulum 201^4 x 31^2 actions"}[args.workload] + f" (BASELINE {args.workload})"
+    if world > 1 and args.scaling == "weak":
+        wl_name += f", axis 0 x{world} (per-GPU slab = the named grid)"
+
+    if args.impl == "reference":
+        run_reference_arm(args, base, wl_name)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from pyro_b200 import problem
+    from pyro_b200.distributed import ShardedEngine
+    from pyro_b200.engine import Engine
+    from tests.cases import build_case
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    _, grid, cf = build_case(case)
+    n, A, N = grid.sys.n, grid.actions_n, grid.nodes_n
+    stream = torch.cuda.current_stream()
+    if world > 1:
+        eng = ShardedEngine(grid, cf, 1.0)
+        kernel_eng = eng.eng
+    else:
+        eng = Engine(problem.extract(grid, cf, 1.0))
+        eng.set_stream(stream.cuda_stream)
+        kernel_eng = eng
+    eng.eval_terminal_cost()
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        eng.sweep(1)
+    barrier()
+
+    # ---- timed region: K sweeps, L2 flushed before each, device time by CUDA events ----------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = kernel_eng.launch_count
+    barrier()
+    t_wall0 = time.perf_counter()
+    for s, e in ev:
+        flush.zero_()            # write 256 MB > L2: the next sweep re-reads J_next from HBM
+        s.record()
+        eng.sweep(1)             # one Bellman sweep (+ all-gather of J for N>1); blocking on its own stats copy
+        e.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    step_ms = np.array([s.elapsed_time(e) for s, e in ev])
+    total_ms = float(step_ms.sum())
+    if world > 1:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    launches = kernel_eng.launch_count - launches0
+    clocks = sampler.stop() if sampler else None
+
+    evals_per_step = float(N) * A
+    value = evals_per_step * args.steps / (total_ms * 1e-3)
+
+    # ---- dominant kernel alone: back-to-back launches on the stream, events around the batch --------
+    kb = max(args.steps, 5)
+    if world == 1:
+        torch.cuda.synchronize()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flush.zero_()
+        k0.record()
+        eng.sweep(kb)
+        k1.record()
+        torch.cuda.synchronize()
+        kernel_ms = k0.elapsed_time(k1) / kb
+    else:
+        kernel_ms = total_ms / args.steps
+    peak, peak_src = measured_peak()
+    slab_evals = evals_per_step / world
+    achieved = slab_evals * b_eval(n, A) / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
+                "kernel": {1: "sweep_pendulum_kernel", 2: "sweep_mech2_kernel<TWOLINK>", 3: "sweep_mech2_kernel<CARTPOLE>"}[kernel_eng.problem.system_id],
+                "kernel_ms": kernel_ms, "algorithmic_bytes_per_eval": b_eval(n, A),
+                "algorithmic_bytes_per_launch": slab_evals * b_eval(n, A),
+                "compulsory_dram_bytes_per_launch": 24.0 * N / world,
+                "note": "contract figure of SURVEY 8(d): the 2^n-corner J gather is served by L1/L2, so DRAM traffic is ~24 B/node "
+                        "and frac can exceed 1; the binding resource is the FP64 pipe (see DESIGN.md, profiles/)"}
+
+    # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        J_host = torch.empty(N, dtype=torch.float64).pin_memory()
+        pi_host = torch.empty(N, dtype=torch.int64).pin_memory()
+        J_host.copy_(torch.from_numpy(eng.get_J()))
+        J_np, pi_np = J_host.numpy(), pi_host.numpy()
+        n_e2e = max(3, min(args.steps, 10))
+        for _ in range(2):
+            eng.set_J(J_np); eng.sweep(1); eng.get_J(J_np); eng.get_pi(pi_np)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            eng.set_J(J_np)        # H2D: J_next, N doubles
+            eng.sweep(1)
+            eng.get_J(J_np)        # D2H: J, N doubles
+            eng.get_pi(pi_np)      # D2H: pi, N int64
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": evals_per_step * n_e2e / dt, "unit": "evals/s", "h2d_bytes_per_step": 8 * N * world,
+               "d2h_bytes_per_step": 16 * N * world, "steps": n_e2e, "ms_per_step": 1e3 * dt / n_e2e,
+               "call": "pdp_set_J + pdp_sweep(1) + pdp_get_J + pdp_get_pi, pinned host buffers"}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------------------------------
+    cpu = cpu_nat = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        nodes = max(1, int(4.0e6 // A))
+        rate, evals, wall = cpu_reference_rate(base, 1, nodes, 5)
+        cpu = {"value": rate, "unit": "evals/s", "cores": 1, "kind": "port",
+               "sample": f"reference LUT sweep (NumPy + scipy RGI, dynamicprogramming.py:564-570) on {nodes} nodes x {A} actions "
+                         f"of the same grid, 5 passes, tables prebuilt; the reference is single-threaded"}
+        nat, thr = cpu_native_rate(base, 1 << 16, 3)
+        cpu_nat = {"value": nat, "unit": "evals/s", "cores": thr, "kind": "port",
+                   "sample": "C/OpenMP restatement oracle/dp_oracle.c, 65536 nodes x all actions x 3 passes, on-the-fly dynamics"}
+
+    if rank == 0:
+        line = {
+            "metric": "state_action_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl_name, "system": case["system"], "x_grid_dim": case["x_grid_dim"],
+                       "u_grid_dim": case["u_grid_dim"], "dt": case["dt"], "alpha": 1.0, "nodes": N, "actions": A,
+                       "evals_per_step": evals_per_step, "parallelism": f"slab{world}" if world > 1 else "single",
+                       "l2": f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)", "J0": "h(x) then warm-up sweeps"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu, "cpu_baseline_native": cpu_nat,
+            "wall_s_timed_region": t_wall, "step_ms_min_max": [float(step_ms.min()), float(step_ms.max())],
+            "J_Linf_error": "see tests/test_parity_gpu.py (bit-exact vs reference goldens)",
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

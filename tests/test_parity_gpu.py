@@ -19,7 +19,8 @@ RTOL = 1e-5  # north_star tolerance on J
 
 
 def rel_err(J, J_ref):
-    return np.abs(J - J_ref).max() / np.abs(J_ref).max()
+    scale = np.abs(J_ref).max()
+    return np.abs(J - J_ref).max() / (scale if scale > 0 else 1.0)
 
 
 @pytest.mark.parametrize("name", list(CASES))
@@ -29,7 +30,7 @@ def test_fused_kernels_match_reference_goldens(name):
     _, grid, cf = build_case(case)
     dp = dynamicprogramming.DynamicProgrammingWithLookUpTable(grid, cf)
     dp.alpha, dp.verbose = case.get("alpha", 1.0), False
-    assert rel_err(dp.J, gold["J0"]) == 0 or np.array_equal(dp.J, gold["J0"])
+    assert np.array_equal(dp.J, gold["J0"])
     k = 0
     for target in case["snapshots"]:
         dp.compute_steps(target - k)
@@ -229,7 +230,7 @@ def test_exact_div_equals_ieee_division():
     lib = C.CDLL(_lib.LIB_PATH)
     rng = np.random.default_rng(5)
     n = 1 << 20
-    den = np.concatenate([np.diff(np.linspace(-2 * np.pi, 2 * np.pi, 1001)).repeat(400)[: n // 2],
+    den = np.concatenate([np.resize(np.diff(np.linspace(-2 * np.pi, 2 * np.pi, 1001)), n // 2),
                           rng.uniform(1e-3, 10.0, n - n // 2)])
     a = den * rng.uniform(0, 1, n)
     a[:1000] = den[:1000]
