@@ -37,7 +37,8 @@ class pdp_stats(C.Structure):
     _fields_ = [("j_max", C.c_double), ("delta_max", C.c_double), ("delta_min", C.c_double)]
 
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpyrodp.so")
+# PYRODP_LIB: development hook to A/B an alternative build of the SAME library (never a fallback)
+LIB_PATH = os.environ.get("PYRODP_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpyrodp.so")
 
 # name -> (restype, argtypes); exactly the symbols include/pyrodp.h declares
 SIGNATURES = {

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -22,240 +23,7 @@
 // Kernels
 // =================================================================================================
 
-#define SWEEP_THREADS 128
-
-// ---- n = 2, 1-dof mechanical system (SinglePendulum) ------------------------------------------
-// One thread per node, lanes along the last (contiguous) axis so the J_next corner reads and the
-// J / pi writes of a warp are contiguous.  Axis-0 of x_next (q + dq*dt) does not depend on the
-// action, so its cell and weight are found once per node; the action loop does the velocity row.
-__global__ void __launch_bounds__(SWEEP_THREADS)
-sweep_pendulum_kernel(const __grid_constant__ DevProblem P, const double* __restrict__ Jn, double* __restrict__ Jo,
-                      long long* __restrict__ pi, double* __restrict__ partials, unsigned int* counter,
-                      double* __restrict__ stats) {
-    extern __shared__ double smem[];
-    const int N0 = P.dims[0], N1 = P.dims[1], A = P.A;
-    double* s_lev1 = smem;               // [N1]
-    double* s_rinv1 = s_lev1 + N1;       // [N1-1] (+1 pad)
-    double* s_bu = s_rinv1 + N1;         // [A]
-    double* s_gu = s_bu + A;             // [A]
-    unsigned char* s_ok = (unsigned char*)(s_gu + A);
-    for (int i = threadIdx.x; i < N1; i += blockDim.x) s_lev1[i] = P.level[1][i];
-    for (int i = threadIdx.x; i < N1 - 1; i += blockDim.x) s_rinv1[i] = P.rinv[1][i];
-    for (int i = threadIdx.x; i < A; i += blockDim.x) {
-        s_bu[i] = P.bu[i];
-        s_gu[i] = P.gu[i];
-        s_ok[i] = P.act_ok[i];
-    }
-    __syncthreads();
-
-    const long long node = P.node_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    Stats3 st = stats_identity();
-    if (node < P.node_end) {
-        const int i0 = (int)(node / N1);
-        const int i1 = (int)(node - (long long)i0 * N1);
-        const double q = __ldg(P.level[0] + i0);
-        const double dq = s_lev1[i1];
-        const double dt = P.dt;
-
-        // position row of x_next: f[0]*dt + x[0] = dq*dt + q (two roundings, discretizer.py:363)
-        const double xn0 = dq * dt + q;
-        const bool pos_ok = !(xn0 < P.lb[0] || xn0 > P.ub[0]);
-
-        double best = P.INF;
-        int besta = 0;
-        if (pos_ok) {
-            const int c0 = find_cell(P.level[0], N0, xn0, P.lb[0], P.inv_step[0]);
-            const double lo0 = __ldg(P.level[0] + c0), hi0 = __ldg(P.level[0] + c0 + 1);
-            const double y0 = (xn0 - lo0) / (hi0 - lo0);
-            const double omy0 = 1.0 - y0;
-            const double* __restrict__ row0 = Jn + (long long)c0 * N1;
-            const double* __restrict__ row1 = row0 + N1;
-
-            // state-only dynamics terms (mechanical.py:222-234)
-            const double grav = __ldg(P.tab[0] + i0);  // g(q)
-            const double Hinv = P.par[0];
-            const double damp = P.par[1] * dq;          // d(q,dq)
-
-            // state-only stage cost (costfunction.py:186-197)
-            double dx[2] = {q - P.xbar[0], dq - P.xbar[1]};
-            bool ontarget = false;
-            double gx = 1.0;
-            if (P.cost_id == PDP_COST_QUADRATIC) gx = quad_form<2>(P.Q, dx);
-            if (P.ontarget_check) ontarget = norm2<2>(dx) < P.EPS;
-
-            const double lb1 = P.lb[1], ub1 = P.ub[1], inv_step1 = P.inv_step[1];
-            best = __longlong_as_double(0x7ff0000000000000LL);
-            for (int a = 0; a < A; ++a) {
-                // ddq = inv(H) . ( B u - C dq - g - d ), C = 0 for this system
-                const double rhs = (s_bu[a] - grav) - damp;
-                const double ddq = Hinv * rhs;
-                const double xn1 = ddq * dt + dq;
-                double Qa = P.INF;
-                if (s_ok[a] && !(xn1 < lb1 || xn1 > ub1)) {
-                    const int c1 = find_cell(s_lev1, N1, xn1, lb1, inv_step1);
-                    const double lo = s_lev1[c1], hi = s_lev1[c1 + 1];
-                    const double y1 = exact_div(xn1 - lo, hi - lo, s_rinv1[c1]);
-                    const double omy1 = 1.0 - y1;
-                    const double v00 = __ldg(row0 + c1), v01 = __ldg(row0 + c1 + 1);
-                    const double v10 = __ldg(row1 + c1), v11 = __ldg(row1 + c1 + 1);
-                    // evaluate_linear_2d (value-first association)
-                    double Jx = v00 * omy0 * omy1;
-                    Jx = Jx + v01 * omy0 * y1;
-                    Jx = Jx + v10 * y0 * omy1;
-                    Jx = Jx + v11 * y0 * y1;
-                    const double g = ontarget ? 0.0 : (gx + s_gu[a]);
-                    Qa = g * dt + (P.alpha_is_one ? Jx : P.alpha * Jx);
-                }
-                if (Qa < best) { best = Qa; besta = a; }
-            }
-        }
-        Jo[node] = best;
-        pi[node] = besta;
-        const double d = best - Jn[node];
-        st.jmax = best; st.dmax = d; st.dmin = d;
-    }
-    block_stats_finish(st, partials, counter, stats);
-}
-
-// ---- n = 4, 2-dof mechanical systems (2-link arm form, cart-pole) --------------------------------
-template <int SYS>
-__global__ void __launch_bounds__(SWEEP_THREADS)
-sweep_mech2_kernel(const __grid_constant__ DevProblem P, const double* __restrict__ Jn, double* __restrict__ Jo,
-                   long long* __restrict__ pi, double* __restrict__ partials, unsigned int* counter,
-                   double* __restrict__ stats) {
-    extern __shared__ double smem[];
-    const int N0 = P.dims[0], N1 = P.dims[1], N2 = P.dims[2], N3 = P.dims[3], A = P.A;
-    double* s_lev2 = smem;             // [N2]
-    double* s_rinv2 = s_lev2 + N2;     // [N2]
-    double* s_lev3 = s_rinv2 + N2;     // [N3]
-    double* s_rinv3 = s_lev3 + N3;     // [N3]
-    double* s_bu = s_rinv3 + N3;       // [2A]
-    double* s_gu = s_bu + 2 * A;       // [A]
-    unsigned char* s_ok = (unsigned char*)(s_gu + A);
-    for (int i = threadIdx.x; i < N2; i += blockDim.x) s_lev2[i] = P.level[2][i];
-    for (int i = threadIdx.x; i < N2 - 1; i += blockDim.x) s_rinv2[i] = P.rinv[2][i];
-    for (int i = threadIdx.x; i < N3; i += blockDim.x) s_lev3[i] = P.level[3][i];
-    for (int i = threadIdx.x; i < N3 - 1; i += blockDim.x) s_rinv3[i] = P.rinv[3][i];
-    for (int i = threadIdx.x; i < A; i += blockDim.x) {
-        s_bu[2 * i] = P.bu[2 * i];
-        s_bu[2 * i + 1] = P.bu[2 * i + 1];
-        s_gu[i] = P.gu[i];
-        s_ok[i] = P.act_ok[i];
-    }
-    __syncthreads();
-
-    const long long node = P.node_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    Stats3 st = stats_identity();
-    if (node < P.node_end) {
-        long long r = node;
-        const int i3 = (int)(r % N3); r /= N3;
-        const int i2 = (int)(r % N2); r /= N2;
-        const int i1 = (int)(r % N1);
-        const int i0 = (int)(r / N1);
-        const double q0 = __ldg(P.level[0] + i0), q1 = __ldg(P.level[1] + i1);
-        const double dq0 = s_lev2[i2], dq1 = s_lev3[i3];
-        const double dt = P.dt;
-
-        // position rows of x_next are action independent: dq*dt + q
-        const double xn0 = dq0 * dt + q0;
-        const double xn1 = dq1 * dt + q1;
-        const bool pos_ok = !(xn0 < P.lb[0] || xn0 > P.ub[0] || xn1 < P.lb[1] || xn1 > P.ub[1]);
-
-        double best = P.INF;
-        int besta = 0;
-        if (pos_ok) {
-            const int c0 = find_cell(P.level[0], N0, xn0, P.lb[0], P.inv_step[0]);
-            const int c1 = find_cell(P.level[1], N1, xn1, P.lb[1], P.inv_step[1]);
-            const double lo0 = __ldg(P.level[0] + c0), hi0 = __ldg(P.level[0] + c0 + 1);
-            const double lo1 = __ldg(P.level[1] + c1), hi1 = __ldg(P.level[1] + c1 + 1);
-            const double y0 = (xn0 - lo0) / (hi0 - lo0);
-            const double y1 = (xn1 - lo1) / (hi1 - lo1);
-            // _evaluate_linear weight-first association: w = (((1*w0)*w1)*w2)*w3 (_rgi.py:543-546)
-            double w01[4];
-            w01[0] = (1.0 - y0) * (1.0 - y1);
-            w01[1] = (1.0 - y0) * y1;
-            w01[2] = y0 * (1.0 - y1);
-            w01[3] = y0 * y1;
-            const long long plane = (long long)N2 * N3;
-            const double* __restrict__ base[4];
-            base[0] = Jn + ((long long)c0 * N1 + c1) * plane;
-            base[1] = base[0] + plane;
-            base[2] = base[0] + (long long)N1 * plane;
-            base[3] = base[2] + plane;
-
-            // ---- state-only dynamics terms: C(q,dq) dq, g(q), d(q,dq), inv(H(q)) ----
-            const double* __restrict__ Hi = P.tab[0] + 4 * i1;
-            const double H00 = __ldg(Hi), H01 = __ldg(Hi + 1), H10 = __ldg(Hi + 2), H11 = __ldg(Hi + 3);
-            double cd0, cd1, g0, g1, d0, d1;
-            if (SYS == PDP_SYS_TWOLINK) {
-                const double h = __ldg(P.tab[1] + i1);
-                const double C00 = (-h) * dq1, C10 = h * dq0, C01 = (-h) * (dq0 + dq1);
-                cd0 = mv2(C00, C01, dq0, dq1);
-                cd1 = mv2(C10, 0.0, dq0, dq1);
-                const double* __restrict__ G = P.tab[2] + 2 * ((long long)i0 * N1 + i1);
-                g0 = __ldg(G); g1 = __ldg(G + 1);
-                d0 = mv2(P.par[0], 0.0, dq0, dq1);
-                d1 = mv2(0.0, P.par[1], dq0, dq1);
-            } else {  // CARTPOLE
-                const double C01 = __ldg(P.tab[1] + i1) * dq1;
-                cd0 = mv2(0.0, C01, dq0, dq1);
-                cd1 = mv2(0.0, 0.0, dq0, dq1);
-                g0 = 0.0; g1 = __ldg(P.tab[2] + i1);
-                d0 = 0.0; d1 = 0.0;
-            }
-
-            // ---- state-only stage cost ----
-            double dx[4] = {q0 - P.xbar[0], q1 - P.xbar[1], dq0 - P.xbar[2], dq1 - P.xbar[3]};
-            bool ontarget = false;
-            double gx = 1.0;
-            if (P.cost_id == PDP_COST_QUADRATIC) gx = quad_form<4>(P.Q, dx);
-            if (P.ontarget_check) ontarget = norm2<4>(dx) < P.EPS;
-
-            const double lb2 = P.lb[2], ub2 = P.ub[2], lb3 = P.lb[3], ub3 = P.ub[3];
-            const double is2 = P.inv_step[2], is3 = P.inv_step[3];
-            best = __longlong_as_double(0x7ff0000000000000LL);
-            for (int a = 0; a < A; ++a) {
-                const double r0 = ((s_bu[2 * a] - cd0) - g0) - d0;
-                const double r1 = ((s_bu[2 * a + 1] - cd1) - g1) - d1;
-                const double ddq0 = mv2(H00, H01, r0, r1);
-                const double ddq1 = mv2(H10, H11, r0, r1);
-                const double xn2 = ddq0 * dt + dq0;
-                const double xn3 = ddq1 * dt + dq1;
-                double Qa = P.INF;
-                if (s_ok[a] && !(xn2 < lb2 || xn2 > ub2 || xn3 < lb3 || xn3 > ub3)) {
-                    const int c2 = find_cell(s_lev2, N2, xn2, lb2, is2);
-                    const int c3 = find_cell(s_lev3, N3, xn3, lb3, is3);
-                    const double l2 = s_lev2[c2], h2 = s_lev2[c2 + 1];
-                    const double l3 = s_lev3[c3], h3 = s_lev3[c3 + 1];
-                    const double y2 = exact_div(xn2 - l2, h2 - l2, s_rinv2[c2]);
-                    const double y3 = exact_div(xn3 - l3, h3 - l3, s_rinv3[c3]);
-                    const double omy2 = 1.0 - y2, omy3 = 1.0 - y3;
-                    const long long o = (long long)c2 * N3 + c3;
-                    double Jx = 0.0;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const double* __restrict__ p = base[k] + o;
-                        const double v00 = __ldg(p), v01 = __ldg(p + 1);
-                        const double v10 = __ldg(p + N3), v11 = __ldg(p + N3 + 1);
-                        const double wa = w01[k] * omy2, wb = w01[k] * y2;
-                        Jx = Jx + v00 * (wa * omy3);
-                        Jx = Jx + v01 * (wa * y3);
-                        Jx = Jx + v10 * (wb * omy3);
-                        Jx = Jx + v11 * (wb * y3);
-                    }
-                    const double g = ontarget ? 0.0 : (gx + s_gu[a]);
-                    Qa = g * dt + (P.alpha_is_one ? Jx : P.alpha * Jx);
-                }
-                if (Qa < best) { best = Qa; besta = a; }
-            }
-        }
-        Jo[node] = best;
-        pi[node] = besta;
-        const double d = best - Jn[node];
-        st.jmax = best; st.dmax = d; st.dmin = d;
-    }
-    block_stats_finish(st, partials, counter, stats);
-}
+#include "sweep_fused.cuh"
 
 // ---- LUT mode: generic n in {2,3,4}, tables in HBM (dynamicprogramming.py:557-570) ---------------
 // A group of G lanes owns one node and strides over its actions, so the x_next / G rows are read
@@ -307,7 +75,7 @@ template <int N, int G>
 __global__ void __launch_bounds__(SWEEP_THREADS)
 sweep_lut_kernel(const __grid_constant__ DevProblem P, const double* __restrict__ Jn, double* __restrict__ Jo,
                  long long* __restrict__ pi, const double* __restrict__ xnext, const double* __restrict__ Gtab,
-                 double* __restrict__ partials, unsigned int* counter, double* __restrict__ stats) {
+                 unsigned long long* __restrict__ partials, unsigned int* counter, double* __restrict__ stats) {
     const int lane_in_group = threadIdx.x % G;
     const long long slot = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;  // node within slab
     const long long node = P.node_begin + slot;
@@ -405,7 +173,7 @@ struct pdp_handle {
     long long* dpi = nullptr;
     double* dstats = nullptr;     // [stats_cap][3]
     int stats_cap = 0;
-    double* dpartials = nullptr;  // [max_blocks][3]
+    unsigned long long* dpartials = nullptr;  // [STATS_SLOTS][3] order-preserving keys (block_stats_finish)
     unsigned int* dcounter = nullptr;
     std::vector<void*> owned;     // small device tables
     double* d_xnext = nullptr;
@@ -418,8 +186,11 @@ struct pdp_handle {
     double last_ms = 0.0;
     int sticky = 0;
     std::string err;
-    int max_blocks = 0;
     size_t smem_bytes = 0;
+    int lanes_per_node = 1;       // G of the fused kernels
+    int force_lanes = 0;          // test hook (PYRODP_LANES): pin G to 1, 4 or 16
+    void* fused = nullptr;        // selected fused kernel instantiation
+    dim3 grid{1, 1, 1};
 };
 
 static thread_local std::string g_err;
@@ -468,6 +239,62 @@ static int expected_tab_len(const pdp_problem* p, int t, long long* len) {
         default: break;
     }
     return 0;
+}
+
+typedef void (*fused_kernel_t)(const DevProblem, const double*, double*, long long*, unsigned long long*, unsigned int*, double*);
+
+template <int G, bool A1>
+static fused_kernel_t fused_for(int system_id) {
+    switch (system_id) {
+        case PDP_SYS_PENDULUM: return sweep_pendulum_kernel<G, A1>;
+        case PDP_SYS_TWOLINK: return sweep_mech2_kernel<PDP_SYS_TWOLINK, G, A1>;
+        case PDP_SYS_CARTPOLE: return sweep_mech2_kernel<PDP_SYS_CARTPOLE, G, A1>;
+    }
+    return nullptr;
+}
+
+// G lanes per node: 1 when the slab alone fills the GPU, else 4 or 16 so that small grids still
+// spread over the 148 SMs (the shuffle argmin keeps np.argmin's first-index rule).
+static int select_fused_kernel(pdp_handle* h, const pdp_problem* p) {
+    DevProblem& P = h->P;
+    const long long slab_nodes = P.node_end - P.node_begin;
+    int sm_count = 148;
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
+    const long long want_threads = (long long)sm_count * 2048;  // one full wave of resident threads
+    int G = 1;
+    if (slab_nodes * 1 < want_threads && P.A >= 4) G = 4;
+    if (slab_nodes * 4 < want_threads && P.A >= 16) G = 16;
+    if (h->force_lanes == 1 || h->force_lanes == 4 || h->force_lanes == 16) G = h->force_lanes;
+    const bool a1 = P.alpha_is_one != 0;
+    fused_kernel_t k = nullptr;
+    if (G == 1) k = a1 ? fused_for<1, true>(P.system_id) : fused_for<1, false>(P.system_id);
+    else if (G == 4) k = a1 ? fused_for<4, true>(P.system_id) : fused_for<4, false>(P.system_id);
+    else k = a1 ? fused_for<16, true>(P.system_id) : fused_for<16, false>(P.system_id);
+    if (!k) return fail(h, PDP_ENOTSUP, "no fused kernel for this system");
+    h->lanes_per_node = G;
+    h->fused = (void*)k;
+    const size_t A = (size_t)P.A;
+    if (P.system_id == PDP_SYS_PENDULUM) {
+        const size_t n1p = (size_t)((P.dims[1] + 1) & ~1);
+        h->smem_bytes = (2 * n1p + 2 * A) * sizeof(double) + 16;
+        const long long threads = slab_nodes * G;
+        const long long blocks = (threads + SWEEP_THREADS - 1) / SWEEP_THREADS;
+        if (blocks > 0x7fffffffLL) return fail(h, PDP_ENOTSUP, "grid too large for one launch");
+        h->grid = dim3((unsigned)(blocks > 0 ? blocks : 1), 1, 1);
+    } else {
+        const size_t n2p = (size_t)((P.dims[2] + 1) & ~1), n3p = (size_t)((P.dims[3] + 1) & ~1);
+        h->smem_bytes = (2 * n2p + 2 * n3p + 4 * A) * sizeof(double) + 16;
+        const long long plane_sz = (long long)P.dims[2] * P.dims[3];
+        const long long chunks = (plane_sz * G + SWEEP_THREADS - 1) / SWEEP_THREADS;
+        const long long planes = (long long)(p->slab_end - p->slab_begin) * P.dims[1];
+        if (plane_sz > 0x7fffffffLL / 16 || chunks > 65535 || planes > 0x7fffffffLL)
+            return fail(h, PDP_ENOTSUP, "grid too large for one launch (dims[2]*dims[3] too big)");
+        h->grid = dim3((unsigned)(planes > 0 ? planes : 1), (unsigned)chunks, 1);
+    }
+    if (h->smem_bytes > 227 * 1024) return fail(h, PDP_ENOTSUP, "level/action tables exceed shared memory (227 KB)");
+    cudaError_t ce = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+    if (ce != cudaSuccess) return fail(h, PDP_ECUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
+    return PDP_OK;
 }
 
 extern "C" int pdp_create(const pdp_problem* p, pdp_handle** out) {
@@ -533,6 +360,11 @@ extern "C" int pdp_create(const pdp_problem* p, pdp_handle** out) {
     h->N_pad = pad_planes * h->plane;
     P.node_begin = (long long)p->slab_begin * h->plane;
     P.node_end = (long long)p->slab_end * h->plane;
+    P.plane_begin = (long long)p->slab_begin * (p->n >= 2 ? p->dims[1] : 1);
+    P.all_act_ok = 1;
+    if (p->system_id != PDP_SYS_LUT)
+        for (long long a = 0; a < A; ++a) if (!p->act_ok[a]) P.all_act_ok = 0;
+    if (const char* env = getenv("PYRODP_LANES")) h->force_lanes = atoi(env);
 
     int rc;
     for (int d = 0; d < p->n; ++d) {
@@ -569,7 +401,12 @@ extern "C" int pdp_create(const pdp_problem* p, pdp_handle** out) {
         if ((rc = upload(h, u_flat.data(), u_flat.size(), &P.u_flat)) != PDP_OK) return bail(rc);
     }
     if (p->system_id != PDP_SYS_LUT) {
-        if ((rc = upload(h, p->bu, (size_t)A * P.dof, &P.bu)) != PDP_OK) return bail(rc);
+        // isavalidinput (system.py:208-215) is folded into the B.u table: a disallowed action carries
+        // NaN, its x_next is NaN, fails the box test and gets Q = INF exactly as dynamicprogramming.py:233
+        std::vector<double> bu(p->bu, p->bu + (size_t)A * P.dof);
+        for (long long a = 0; a < A; ++a)
+            if (!p->act_ok[a]) for (int d = 0; d < P.dof; ++d) bu[(size_t)a * P.dof + d] = __builtin_nan("");
+        if ((rc = upload(h, bu.data(), bu.size(), &P.bu)) != PDP_OK) return bail(rc);
         if ((rc = upload(h, p->gu, (size_t)A, &P.gu)) != PDP_OK) return bail(rc);
         if ((rc = upload(h, (const unsigned char*)p->act_ok, (size_t)A, &P.act_ok)) != PDP_OK) return bail(rc);
     }
@@ -583,12 +420,8 @@ extern "C" int pdp_create(const pdp_problem* p, pdp_handle** out) {
     if (!cu(cudaMalloc(&h->dpi, h->N * sizeof(long long)), "cudaMalloc pi")) return bail(PDP_ECUDA);
     h->stats_cap = 256;
     if (!cu(cudaMalloc(&h->dstats, h->stats_cap * 3 * sizeof(double)), "cudaMalloc stats")) return bail(PDP_ECUDA);
-    const long long slab_nodes = P.node_end - P.node_begin;
-    // worst case blocks: LUT kernel with 32 lanes per node
-    long long maxb = (slab_nodes * 32 + SWEEP_THREADS - 1) / SWEEP_THREADS + 1;
-    if (p->system_id != PDP_SYS_LUT) maxb = (slab_nodes + SWEEP_THREADS - 1) / SWEEP_THREADS + 1;
-    h->max_blocks = (int)maxb;
-    if (!cu(cudaMalloc(&h->dpartials, (size_t)maxb * 3 * sizeof(double)), "cudaMalloc partials")) return bail(PDP_ECUDA);
+    if (!cu(cudaMalloc(&h->dpartials, 3 * STATS_SLOTS * sizeof(unsigned long long)), "cudaMalloc stats slots")) return bail(PDP_ECUDA);
+    if (!cu(cudaMemset(h->dpartials, 0, 3 * STATS_SLOTS * sizeof(unsigned long long)), "cudaMemset stats slots")) return bail(PDP_ECUDA);
     if (!cu(cudaMalloc(&h->dcounter, sizeof(unsigned int)), "cudaMalloc counter")) return bail(PDP_ECUDA);
     if (!cu(cudaMemset(h->dcounter, 0, sizeof(unsigned int)), "cudaMemset counter")) return bail(PDP_ECUDA);
     if (!cu(cudaMemset(h->dpi, 0, h->N * sizeof(long long)), "cudaMemset pi")) return bail(PDP_ECUDA);
@@ -597,16 +430,10 @@ extern "C" int pdp_create(const pdp_problem* p, pdp_handle** out) {
     if (!cu(cudaEventCreate(&h->ev0), "cudaEventCreate")) return bail(PDP_ECUDA);
     if (!cu(cudaEventCreate(&h->ev1), "cudaEventCreate")) return bail(PDP_ECUDA);
 
-    // dynamic shared memory of the fused kernels
-    if (p->system_id == PDP_SYS_PENDULUM) {
-        h->smem_bytes = (size_t)(2 * p->dims[1] + 2 * A) * sizeof(double) + (size_t)A + 16;
-        if (!cu(cudaFuncSetAttribute(sweep_pendulum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes), "smem attr")) return bail(PDP_ECUDA);
-    } else if (p->system_id == PDP_SYS_TWOLINK || p->system_id == PDP_SYS_CARTPOLE) {
-        h->smem_bytes = (size_t)(2 * p->dims[2] + 2 * p->dims[3] + 3 * A) * sizeof(double) + (size_t)A + 16;
-        cudaError_t ce = (p->system_id == PDP_SYS_TWOLINK)
-                             ? cudaFuncSetAttribute(sweep_mech2_kernel<PDP_SYS_TWOLINK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes)
-                             : cudaFuncSetAttribute(sweep_mech2_kernel<PDP_SYS_CARTPOLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
-        if (!cu(ce, "smem attr")) return bail(PDP_ECUDA);
+    // fused kernels: lanes per node, grid shape, kernel instantiation, dynamic shared memory
+    if (p->system_id != PDP_SYS_LUT) {
+        int rcsel = select_fused_kernel(h, p);
+        if (rcsel != PDP_OK) return bail(rcsel);
     }
     *out = h;
     return PDP_OK;
@@ -747,13 +574,7 @@ static int launch_sweep(pdp_handle* h, double* stats) {
         else if (P.n == 3) launch_lut<3>(h, G, blocks, Jn, Jo, stats);
         else launch_lut<4>(h, G, blocks, Jn, Jo, stats);
     } else {
-        const unsigned blocks = (unsigned)((slab_nodes + SWEEP_THREADS - 1) / SWEEP_THREADS);
-        if (P.system_id == PDP_SYS_PENDULUM)
-            sweep_pendulum_kernel<<<blocks, SWEEP_THREADS, h->smem_bytes, h->stream>>>(P, Jn, Jo, h->dpi, h->dpartials, h->dcounter, stats);
-        else if (P.system_id == PDP_SYS_TWOLINK)
-            sweep_mech2_kernel<PDP_SYS_TWOLINK><<<blocks, SWEEP_THREADS, h->smem_bytes, h->stream>>>(P, Jn, Jo, h->dpi, h->dpartials, h->dcounter, stats);
-        else
-            sweep_mech2_kernel<PDP_SYS_CARTPOLE><<<blocks, SWEEP_THREADS, h->smem_bytes, h->stream>>>(P, Jn, Jo, h->dpi, h->dpartials, h->dcounter, stats);
+        ((fused_kernel_t)h->fused)<<<h->grid, SWEEP_THREADS, h->smem_bytes, h->stream>>>(P, Jn, Jo, h->dpi, h->dpartials, h->dcounter, stats);
     }
     CUDA_TRY(h, cudaGetLastError());
     h->launches += 1;

@@ -13,6 +13,7 @@
 struct DevProblem {
     int n, m, dof, A;
     int system_id, cost_id, ontarget_check, alpha_is_one;
+    int all_act_ok, pad0;           // every action passes isavalidinput (the usual case)
     int dims[PDP_MAXN];
     long long stride[PDP_MAXN];     // node-id stride of each axis (C order)
     const double* level[PDP_MAXN];  // device copies of np.linspace levels
@@ -26,6 +27,7 @@ struct DevProblem {
     const unsigned char* act_ok;  // [A]
     const double* u_flat;      // [A*m] input_from_action_id
     long long node_begin, node_end, N;
+    long long plane_begin;          // first (i0,i1) pair of the slab = slab_begin * dims[1] (4-D kernels)
 };
 
 // ---- np.dot conventions of the reference's BLAS (OpenBLAS 0.3.30 SkylakeX kernels) -----------
@@ -121,15 +123,31 @@ __device__ __forceinline__ Stats3 warp_stats(Stats3 s) {
     return s;
 }
 
-// Block reduce, write one partial per block, last block folds all partials into out[3].
-// `counter` must be zero at launch; the last block resets it.
-__device__ __forceinline__ void block_stats_finish(Stats3 s, double* __restrict__ partials, unsigned int* counter,
+// Order-preserving map double -> uint64 so that max/min run as integer atomics (RED.MAX.U64).
+__device__ __forceinline__ unsigned long long stats_key(double x) {
+    const unsigned long long u = (unsigned long long)__double_as_longlong(x);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ULL);
+}
+__device__ __forceinline__ double stats_unkey(unsigned long long k) {
+    const unsigned long long u = (k >> 63) ? (k & 0x7fffffffffffffffULL) : ~k;
+    return __longlong_as_double((long long)u);
+}
+
+#define STATS_SLOTS 64
+// Block reduce -> three RED.MAX.U64 into one of STATS_SLOTS slot triples {key(jmax), key(dmax),
+// key(-dmin)} (spread by block id to keep the L2 atomic unit off a single address) -> ticket;
+// the last block folds the slots, decodes into out[3] = {max J, max dJ, min dJ}
+// (finalize_backward_step, dynamicprogramming.py:247-250) and re-arms slots and ticket.
+// `slots` (3*STATS_SLOTS u64) and `counter` must be zero at launch.
+__device__ __forceinline__ void block_stats_finish(Stats3 s, unsigned long long* __restrict__ slots, unsigned int* counter,
                                                    double* __restrict__ out) {
     __shared__ Stats3 sh[32];
     __shared__ bool is_last;
     const int tid = threadIdx.x + threadIdx.y * blockDim.x;
     const int nthreads = blockDim.x * blockDim.y;
     const int lane = tid & 31, warp = tid >> 5, nwarps = (nthreads + 31) >> 5;
+    const unsigned int bid = blockIdx.x + blockIdx.y * gridDim.x;
+    const unsigned int nblocks = gridDim.x * gridDim.y;
     s = warp_stats(s);
     if (lane == 0) sh[warp] = s;
     __syncthreads();
@@ -137,38 +155,36 @@ __device__ __forceinline__ void block_stats_finish(Stats3 s, double* __restrict_
         Stats3 t = lane < nwarps ? sh[lane] : stats_identity();
         t = warp_stats(t);
         if (lane == 0) {
-            partials[3 * blockIdx.x + 0] = t.jmax;
-            partials[3 * blockIdx.x + 1] = t.dmax;
-            partials[3 * blockIdx.x + 2] = t.dmin;
+            unsigned long long* slot = slots + 3 * (bid % STATS_SLOTS);
+            atomicMax(slot + 0, stats_key(t.jmax));
+            atomicMax(slot + 1, stats_key(t.dmax));
+            atomicMax(slot + 2, stats_key(-t.dmin));
             __threadfence();
-            unsigned int ticket = atomicAdd(counter, 1u);
-            is_last = (ticket == gridDim.x - 1);
+            const unsigned int ticket = atomicAdd(counter, 1u);
+            is_last = (ticket == nblocks - 1);
         }
     }
     __syncthreads();
-    if (is_last) {
+    if (is_last && warp == 0) {
         __threadfence();
-        Stats3 t = stats_identity();
-        for (int b = tid; b < (int)gridDim.x; b += nthreads) {
-            Stats3 o;
-            o.jmax = __ldcg(&partials[3 * b + 0]);
-            o.dmax = __ldcg(&partials[3 * b + 1]);
-            o.dmin = __ldcg(&partials[3 * b + 2]);
-            stats_merge(t, o);
+        unsigned long long k0 = 0, k1 = 0, k2 = 0;
+        for (int b = lane; b < STATS_SLOTS; b += 32) {
+            k0 = max(k0, __ldcg(slots + 3 * b + 0));
+            k1 = max(k1, __ldcg(slots + 3 * b + 1));
+            k2 = max(k2, __ldcg(slots + 3 * b + 2));
+            slots[3 * b + 0] = 0; slots[3 * b + 1] = 0; slots[3 * b + 2] = 0;
         }
-        t = warp_stats(t);
-        __syncthreads();
-        if (lane == 0) sh[warp] = t;
-        __syncthreads();
-        if (warp == 0) {
-            Stats3 u = lane < nwarps ? sh[lane] : stats_identity();
-            u = warp_stats(u);
-            if (lane == 0) {
-                out[0] = u.jmax;
-                out[1] = u.dmax;
-                out[2] = u.dmin;
-                *counter = 0u;
-            }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            k0 = max(k0, __shfl_xor_sync(0xffffffffu, k0, off));
+            k1 = max(k1, __shfl_xor_sync(0xffffffffu, k1, off));
+            k2 = max(k2, __shfl_xor_sync(0xffffffffu, k2, off));
+        }
+        if (lane == 0) {
+            out[0] = stats_unkey(k0);
+            out[1] = stats_unkey(k1);
+            out[2] = -stats_unkey(k2);
+            *counter = 0u;
         }
     }
 }

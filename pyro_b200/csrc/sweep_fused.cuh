@@ -1,0 +1,355 @@
+// Fused on-the-fly Bellman sweep kernels (the north-star kernels), sm_100a.
+//
+// Replaces, per launch, one full sweep of
+//   pyro/planning/dynamicprogramming.py:175-261 (initialize / compute / finalize_backward_step)
+// with the dynamics evaluated on the fly as the base class does (:195-236) instead of the
+// (N,A,n) x_next_table of the LUT variant (:557-570, discretizer.py:342-376).
+//
+// Mapping.  A group of G lanes owns one node; lanes of a group stride over the actions and the
+// min/argmin over actions ends in a warp-shuffle reduction with lowest-index tie break
+// (np.argmin, :236).  G = 1 for large grids (a thread scans all actions of its node, no
+// reduction needed), G > 1 when the grid alone cannot fill 148 SMs.  Consecutive groups walk the
+// last (contiguous) grid axis, so the J_next corner gathers of a warp fall into 2-3 cache lines
+// and the J / pi stores are contiguous.
+//
+// Inner loop economy (ncu, profiles/): the sweep is bound by issue slots, the FP64 pipe and L1
+// wavefronts, not by HBM.  Per action the loop therefore
+//   * reads one packed record {B.u, du'R du} from shared memory (broadcast, one wavefront),
+//   * keeps the current interpolation cell of every action-dependent axis in registers
+//     {index, lo, hi, 1/(hi-lo)} and only walks it when x_next leaves the cell — the level table
+//     decides, so the result equals scipy's binary search (find_interval_ascending),
+//   * forms the normalised distance with the 3-instruction correctly rounded quotient exact_div,
+//   * gathers the 2^n corners through the read-only path with immediate offsets.
+#pragma once
+#include "pyrodp_device.cuh"
+
+#define SWEEP_THREADS 128
+
+// ---- register-cached interpolation cell of one axis --------------------------------------------
+struct CellCache {
+    int c;
+    double lo, hi, rinv;
+};
+
+// (re)position the cell so that lev[c] <= x < lev[c+1] (last cell closed on the right).
+// Caller guarantees lev[0] <= x <= lev[nlev-1].  Identical to find_cell / scipy's search: the
+// level table decides.  Fast paths: same cell (2 compares), neighbouring cell (one table read);
+// otherwise an arithmetic guess followed by a table-checked walk of at most a step or two.
+__device__ __forceinline__ void cell_seek(CellCache& cc, const double* __restrict__ s_lev,
+                                          const double* __restrict__ s_rinv, int nlev, double x, double lb,
+                                          double inv_step) {
+    if (x >= cc.hi || x < cc.lo) {
+        int c = min(max(cc.c + (x >= cc.hi ? 1 : -1), 0), nlev - 2);
+        double lo = s_lev[c], hi = s_lev[c + 1];
+        if (x >= hi || x < lo) {
+            c = min(max((int)((x - lb) * inv_step), 0), nlev - 2);
+            lo = s_lev[c]; hi = s_lev[c + 1];
+            while (x < lo && c > 0) { --c; hi = lo; lo = s_lev[c]; }
+            while (x >= hi && c < nlev - 2) { ++c; lo = hi; hi = s_lev[c + 1]; }
+        }
+        cc.c = c; cc.lo = lo; cc.hi = hi;
+        cc.rinv = s_rinv[c];
+    }
+}
+
+__device__ __forceinline__ void cell_init(CellCache& cc, const double* __restrict__ s_lev,
+                                          const double* __restrict__ s_rinv, int nlev, int guess) {
+    cc.c = min(max(guess, 0), nlev - 2);
+    cc.lo = s_lev[cc.c];
+    cc.hi = s_lev[cc.c + 1];
+    cc.rinv = s_rinv[cc.c];
+}
+
+// Make a pointer opaque to the optimiser, so that ptr[int_index] compiles to one IMAD.WIDE from a
+// register-resident base instead of re-deriving base + 64-bit element offset per access (SASS
+// showed four integer instructions per gather address without it).
+template <typename T>
+__device__ __forceinline__ const T* opaque(const T* p) {
+    asm("" : "+l"(p));
+    return p;
+}
+
+// Pin a loop constant in a register.  ptxas otherwise re-reads kernel parameters from the
+// constant bank inside the action loop (five LDC per eval in the first SASS); OR-ing in a
+// run-time zero (blockIdx.z of a grid whose z extent is 1) makes the value a computed one.
+__device__ __forceinline__ double pinned(double x) {
+    return __longlong_as_double(__double_as_longlong(x) | (long long)blockIdx.z);
+}
+
+// ---- shared-memory staging of the small tables -------------------------------------------------
+__device__ __forceinline__ void stage(double* dst, const double* __restrict__ src, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldg(src + i);
+}
+
+// =================================================================================================
+// n = 2, 1-dof mechanical system (pyro/dynamic/pendulum.py:16 SinglePendulum)
+// =================================================================================================
+template <int G, bool ALPHA1>
+__global__ void __launch_bounds__(SWEEP_THREADS)
+sweep_pendulum_kernel(const __grid_constant__ DevProblem P, const double* __restrict__ Jn, double* __restrict__ Jo,
+                      long long* __restrict__ pi, unsigned long long* __restrict__ partials, unsigned int* counter,
+                      double* __restrict__ stats) {
+    extern __shared__ __align__(16) double smem[];
+    const int N0 = P.dims[0], N1 = P.dims[1], A = P.A;
+    const int N1p = (N1 + 1) & ~1;
+    double* s_lev1 = smem;                       // [N1p]
+    double* s_rinv1 = s_lev1 + N1p;              // [N1p]
+    double2* s_act = (double2*)(s_rinv1 + N1p);  // [A] {B.u (NaN when isavalidinput fails), du'R du}
+    stage(s_lev1, P.level[1], N1);
+    stage(s_rinv1, P.rinv[1], N1 - 1);
+    for (int i = threadIdx.x; i < A; i += blockDim.x) s_act[i] = make_double2(__ldg(P.bu + i), __ldg(P.gu + i));
+    __syncthreads();
+
+    const long long slot = ((long long)blockIdx.x * SWEEP_THREADS + threadIdx.x) / G;
+    const int g = threadIdx.x % G;
+    const long long node = P.node_begin + slot;
+    const bool active = node < P.node_end;
+    Stats3 st = stats_identity();
+    double best = __longlong_as_double(0x7ff0000000000000LL);
+    int besta = 0x7fffffff;
+    if (active) {
+        const int i0 = (int)(node / N1);
+        const int i1 = (int)(node - (long long)i0 * N1);
+        const double q = __ldg(P.level[0] + i0);
+        const double dq = s_lev1[i1];
+        const double dt = pinned(P.dt);
+
+        // position row of x_next: f[0]*dt + x[0] = dq*dt + q (two roundings, discretizer.py:363)
+        const double xn0 = dq * dt + q;
+        const bool pos_ok = !(xn0 < P.lb[0] || xn0 > P.ub[0]);
+        if (pos_ok) {
+            const int c0 = find_cell(P.level[0], N0, xn0, P.lb[0], P.inv_step[0]);
+            const double lo0 = __ldg(P.level[0] + c0), hi0 = __ldg(P.level[0] + c0 + 1);
+            const double y0 = (xn0 - lo0) / (hi0 - lo0);
+            const double omy0 = pinned(1.0 - y0);
+            const double* __restrict__ row0 = opaque(Jn + (long long)c0 * N1);
+            const double* __restrict__ row1 = opaque(row0 + N1);
+
+            // state-only dynamics terms (mechanical.py:222-234): g(q), inv(H), d(q,dq); C = 0
+            const double grav = __ldg(P.tab[0] + i0);
+            const double Hinv = pinned(P.par[0]);
+            const double damp = P.par[1] * dq;
+
+            // state-only stage cost (costfunction.py:186-197)
+            const double dx[2] = {q - P.xbar[0], dq - P.xbar[1]};
+            double gx = 1.0;
+            if (P.cost_id == PDP_COST_QUADRATIC) gx = quad_form<2>(P.Q, dx);
+            const bool ontarget = P.ontarget_check && (norm2<2>(dx) < P.EPS);
+
+            // loop constants pinned in registers (else ptxas re-reads the constant bank per action)
+            const double lb1 = pinned(P.lb[1]), ub1 = pinned(P.ub[1]), is1 = P.inv_step[1];
+            const double INF = pinned(P.INF), alpha = P.alpha;
+            // g = 0 inside the target zone (costfunction.py:193-197): 0*dt == (gx+gu)*0 == +0
+            const double dt_cost = ontarget ? 0.0 : dt;
+            CellCache c1;
+            cell_init(c1, s_lev1, s_rinv1, N1, i1);
+#pragma unroll 2
+            for (int a = g; a < A; a += G) {
+                const double2 act = s_act[a];
+                // ddq = inv(H) . (B u - C dq - g - d)
+                const double rhs = (act.x - grav) - damp;
+                const double ddq = Hinv * rhs;
+                const double xn1 = ddq * dt + dq;
+                double Qa = INF;
+                // isavalidstate (system.py:198-205); a NaN from a disallowed action fails both tests
+                if (xn1 >= lb1 && xn1 <= ub1) {
+                    cell_seek(c1, s_lev1, s_rinv1, N1, xn1, lb1, is1);
+                    const double y1 = exact_div(xn1 - c1.lo, c1.hi - c1.lo, c1.rinv);
+                    const double omy1 = 1.0 - y1;
+                    const double* __restrict__ p0 = row0 + c1.c;
+                    const double* __restrict__ p1 = row1 + c1.c;
+                    const double v00 = __ldg(p0), v01 = __ldg(p0 + 1);
+                    const double v10 = __ldg(p1), v11 = __ldg(p1 + 1);
+                    // evaluate_linear_2d: value-first association
+                    double Jx = v00 * omy0 * omy1;
+                    Jx = Jx + v01 * omy0 * y1;
+                    Jx = Jx + v10 * y0 * omy1;
+                    Jx = Jx + v11 * y0 * y1;
+                    Qa = (gx + act.y) * dt_cost + (ALPHA1 ? Jx : alpha * Jx);
+                }
+                if (Qa < best) { best = Qa; besta = a; }
+            }
+        } else if (g == 0) {
+            best = P.INF;  // every action leaves the box: Q = INF for all, argmin = 0
+            besta = 0;
+        }
+    }
+    if (G > 1) lane_group_argmin(best, besta, G);
+    if (active && g == 0) {
+        Jo[node] = best;
+        pi[node] = besta;
+        const double d = best - Jn[node];
+        st.jmax = best; st.dmax = d; st.dmin = d;
+    }
+    block_stats_finish(st, partials, counter, stats);
+}
+
+// =================================================================================================
+// n = 4, 2-dof mechanical systems: 2-link arm form (pendulum.py:340 DoublePendulum,
+// manipulator.py:795 TwoLinkManipulator) and cart-pole (cartpole.py:322)
+// grid: blockIdx.x = (i0,i1) plane of the slab, blockIdx.y = chunk of the (i2,i3) plane
+// =================================================================================================
+#ifndef MECH2_MIN_BLOCKS
+#define MECH2_MIN_BLOCKS 4
+#endif
+template <int SYS, int G, bool ALPHA1>
+__global__ void __launch_bounds__(SWEEP_THREADS, MECH2_MIN_BLOCKS)
+sweep_mech2_kernel(const __grid_constant__ DevProblem P, const double* __restrict__ Jn, double* __restrict__ Jo,
+                   long long* __restrict__ pi, unsigned long long* __restrict__ partials, unsigned int* counter,
+                   double* __restrict__ stats) {
+    extern __shared__ __align__(16) double smem[];
+    const int N0 = P.dims[0], N1 = P.dims[1], N2 = P.dims[2], N3 = P.dims[3], A = P.A;
+    const int N2p = (N2 + 1) & ~1, N3p = (N3 + 1) & ~1;
+    double* s_lev2 = smem;              // [N2p]
+    double* s_rinv2 = s_lev2 + N2p;     // [N2p]
+    double* s_lev3 = s_rinv2 + N2p;     // [N3p]
+    double* s_rinv3 = s_lev3 + N3p;     // [N3p]
+    double2* s_act = (double2*)(s_rinv3 + N3p);  // [2A] {B.u[0], B.u[1]} (NaN when isavalidinput fails), {du'R du, -}
+    stage(s_lev2, P.level[2], N2);
+    stage(s_rinv2, P.rinv[2], N2 - 1);
+    stage(s_lev3, P.level[3], N3);
+    stage(s_rinv3, P.rinv[3], N3 - 1);
+    for (int i = threadIdx.x; i < A; i += blockDim.x) {
+        s_act[2 * i] = make_double2(__ldg(P.bu + 2 * i), __ldg(P.bu + 2 * i + 1));
+        s_act[2 * i + 1] = make_double2(__ldg(P.gu + i), 0.0);
+    }
+    __syncthreads();
+
+    // block-uniform part of the node index
+    const int plane_sz = N2 * N3;                                  // checked on the host: < 2^31
+    const long long pl = P.plane_begin + (long long)blockIdx.x;   // (i0,i1) pair, C order
+    const int i0 = (int)(pl / N1);
+    const int i1 = (int)(pl - (long long)i0 * N1);
+    const int r = (int)(((unsigned)blockIdx.y * SWEEP_THREADS + threadIdx.x) / G);  // (i2,i3) within the plane
+    const int g = threadIdx.x % G;
+    const bool active = r < plane_sz;
+    const long long node = pl * plane_sz + r;
+    Stats3 st = stats_identity();
+    double best = __longlong_as_double(0x7ff0000000000000LL);
+    int besta = 0x7fffffff;
+    if (active) {
+        const int i2 = r / N3;
+        const int i3 = r - i2 * N3;
+        const double q0 = __ldg(P.level[0] + i0), q1 = __ldg(P.level[1] + i1);
+        const double dq0 = s_lev2[i2], dq1 = s_lev3[i3];
+        const double dt = P.dt;
+
+        // position rows of x_next are action independent: dq*dt + q
+        const double xn0 = dq0 * dt + q0;
+        const double xn1 = dq1 * dt + q1;
+        const bool pos_ok = !(xn0 < P.lb[0] || xn0 > P.ub[0] || xn1 < P.lb[1] || xn1 > P.ub[1]);
+        if (pos_ok) {
+            const int c0 = find_cell(P.level[0], N0, xn0, P.lb[0], P.inv_step[0]);
+            const int c1 = find_cell(P.level[1], N1, xn1, P.lb[1], P.inv_step[1]);
+            const double lo0 = __ldg(P.level[0] + c0), hi0 = __ldg(P.level[0] + c0 + 1);
+            const double lo1 = __ldg(P.level[1] + c1), hi1 = __ldg(P.level[1] + c1 + 1);
+            const double y0 = (xn0 - lo0) / (hi0 - lo0);
+            const double y1 = (xn1 - lo1) / (hi1 - lo1);
+            // _evaluate_linear weight-first association: w = (((1*w0)*w1)*w2)*w3 (_rgi.py:543-546)
+            const double w00 = (1.0 - y0) * (1.0 - y1), w01 = (1.0 - y0) * y1;
+            const double w10 = y0 * (1.0 - y1), w11 = y0 * y1;
+            const double* __restrict__ b00 = opaque(Jn + ((long long)c0 * N1 + c1) * plane_sz);
+            const double* __restrict__ b01 = opaque(b00 + plane_sz);
+            const double* __restrict__ b10 = opaque(b00 + (long long)N1 * plane_sz);
+            const double* __restrict__ b11 = opaque(b10 + plane_sz);
+
+            // ---- state-only dynamics terms: C(q,dq) dq, g(q), d(q,dq), inv(H(q)) ----
+            const double* __restrict__ Hi = P.tab[0] + 4 * i1;
+            const double H00 = __ldg(Hi), H01 = __ldg(Hi + 1), H10 = __ldg(Hi + 2), H11 = __ldg(Hi + 3);
+            double cd0, cd1, g0, g1, d0, d1;
+            if (SYS == PDP_SYS_TWOLINK) {
+                const double h = __ldg(P.tab[1] + i1);
+                const double C00 = (-h) * dq1, C10 = h * dq0, C01 = (-h) * (dq0 + dq1);
+                cd0 = mv2(C00, C01, dq0, dq1);
+                cd1 = mv2(C10, 0.0, dq0, dq1);
+                const double* __restrict__ Gq = P.tab[2] + 2 * ((long long)i0 * N1 + i1);
+                g0 = __ldg(Gq); g1 = __ldg(Gq + 1);
+                d0 = mv2(P.par[0], 0.0, dq0, dq1);
+                d1 = mv2(0.0, P.par[1], dq0, dq1);
+            } else {  // CARTPOLE
+                const double C01 = __ldg(P.tab[1] + i1) * dq1;
+                cd0 = mv2(0.0, C01, dq0, dq1);
+                cd1 = mv2(0.0, 0.0, dq0, dq1);
+                g0 = 0.0; g1 = __ldg(P.tab[2] + i1);
+                d0 = 0.0; d1 = 0.0;
+            }
+
+            // ---- state-only stage cost ----
+            const double dx[4] = {q0 - P.xbar[0], q1 - P.xbar[1], dq0 - P.xbar[2], dq1 - P.xbar[3]};
+            double gx = 1.0;
+            if (P.cost_id == PDP_COST_QUADRATIC) gx = quad_form<4>(P.Q, dx);
+            const bool ontarget = P.ontarget_check && (norm2<4>(dx) < P.EPS);
+
+            const double lb2 = P.lb[2], ub2 = P.ub[2], lb3 = P.lb[3], ub3 = P.ub[3];
+            const double is2 = P.inv_step[2], is3 = P.inv_step[3];
+            const double INF = P.INF, alpha = P.alpha;
+            const double dt_cost = ontarget ? 0.0 : dt;
+            CellCache k2, k3;
+            cell_init(k2, s_lev2, s_rinv2, N2, i2);
+            cell_init(k3, s_lev3, s_rinv3, N3, i3);
+            for (int a = g; a < A; a += G) {
+                const double2 bu = s_act[2 * a];
+                // B u - C dq - g - d, left to right (mechanical.py:231).  For the cart-pole g[0], d[0]
+                // and d[1] are literal zeros (cartpole.py:415-437) and x - 0.0 == x bit for bit.
+                const double r0 = (SYS == PDP_SYS_CARTPOLE) ? (bu.x - cd0) : (((bu.x - cd0) - g0) - d0);
+                const double r1 = (SYS == PDP_SYS_CARTPOLE) ? ((bu.y - cd1) - g1) : (((bu.y - cd1) - g1) - d1);
+                const double ddq0 = mv2(H00, H01, r0, r1);
+                const double ddq1 = mv2(H10, H11, r0, r1);
+                const double xn2 = ddq0 * dt + dq0;
+                const double xn3 = ddq1 * dt + dq1;
+                double Qa = INF;
+                if (xn2 >= lb2 && xn2 <= ub2 && xn3 >= lb3 && xn3 <= ub3) {
+                    cell_seek(k2, s_lev2, s_rinv2, N2, xn2, lb2, is2);
+                    cell_seek(k3, s_lev3, s_rinv3, N3, xn3, lb3, is3);
+                    const double y2 = exact_div(xn2 - k2.lo, k2.hi - k2.lo, k2.rinv);
+                    const double y3 = exact_div(xn3 - k3.lo, k3.hi - k3.lo, k3.rinv);
+                    const double omy2 = 1.0 - y2, omy3 = 1.0 - y3;
+                    const int o = k2.c * N3 + k3.c;
+                    const int o2 = o + N3;
+                    double Jx;
+                    {   // corners in itertools.product order: axis 0 slowest, offset 0 before 1
+                        const double wa = w00 * omy2, wb = w00 * y2;
+                        Jx = 0.0 + __ldg(b00 + o) * (wa * omy3);  // value = 0 + term (_rgi.py:528,547)
+                        Jx = Jx + __ldg(b00 + o + 1) * (wa * y3);
+                        Jx = Jx + __ldg(b00 + o2) * (wb * omy3);
+                        Jx = Jx + __ldg(b00 + o2 + 1) * (wb * y3);
+                    }
+                    {
+                        const double wa = w01 * omy2, wb = w01 * y2;
+                        Jx = Jx + __ldg(b01 + o) * (wa * omy3);
+                        Jx = Jx + __ldg(b01 + o + 1) * (wa * y3);
+                        Jx = Jx + __ldg(b01 + o2) * (wb * omy3);
+                        Jx = Jx + __ldg(b01 + o2 + 1) * (wb * y3);
+                    }
+                    {
+                        const double wa = w10 * omy2, wb = w10 * y2;
+                        Jx = Jx + __ldg(b10 + o) * (wa * omy3);
+                        Jx = Jx + __ldg(b10 + o + 1) * (wa * y3);
+                        Jx = Jx + __ldg(b10 + o2) * (wb * omy3);
+                        Jx = Jx + __ldg(b10 + o2 + 1) * (wb * y3);
+                    }
+                    {
+                        const double wa = w11 * omy2, wb = w11 * y2;
+                        Jx = Jx + __ldg(b11 + o) * (wa * omy3);
+                        Jx = Jx + __ldg(b11 + o + 1) * (wa * y3);
+                        Jx = Jx + __ldg(b11 + o2) * (wb * omy3);
+                        Jx = Jx + __ldg(b11 + o2 + 1) * (wb * y3);
+                    }
+                    Qa = (gx + s_act[2 * a + 1].x) * dt_cost + (ALPHA1 ? Jx : alpha * Jx);
+                }
+                if (Qa < best) { best = Qa; besta = a; }
+            }
+        } else if (g == 0) {
+            best = P.INF;
+            besta = 0;
+        }
+    }
+    if (G > 1) lane_group_argmin(best, besta, G);
+    if (active && g == 0) {
+        Jo[node] = best;
+        pi[node] = besta;
+        const double d = best - Jn[node];
+        st.jmax = best; st.dmax = d; st.dmin = d;
+    }
+    block_stats_finish(st, partials, counter, stats);
+}

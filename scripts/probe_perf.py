@@ -13,6 +13,8 @@ CASES = {
     "dp61": ("DoublePendulum", [61] * 4, [31, 31], None, 1000.0, 0.05),
     "cfg3": ("TwoLinkManipulator", [101] * 4, [21, 21], None, 1000.0, 0.05),
     "cfg4": ("CartPole", [151] * 4, [51], [0, np.pi, 0, 0], 1000.0, 0.05),
+    "cfg5": ("DoublePendulum", [201] * 4, [31, 31], None, 1000.0, 0.05),
+    "cp61": ("CartPole", [61] * 4, [51], [0, np.pi, 0, 0], 1000.0, 0.05),
 }
 
 def main():
@@ -28,8 +30,9 @@ def main():
         t0 = time.time()
         eng = Engine(problem.extract(g, cf, 1.0))
         eng.eval_terminal_cost()
-        eng.sweep(3)
-        K = 10 if g.nodes_n * g.actions_n < 5e9 else 3
+        evals_ = g.nodes_n * g.actions_n
+        eng.sweep(3 if evals_ < 1e11 else 1)
+        K = 10 if evals_ < 5e9 else (3 if evals_ < 1e11 else 1)
         st = eng.sweep(K)
         ms = eng.last_sweep_ms / K
         evals = g.nodes_n * g.actions_n
