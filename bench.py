@@ -15,7 +15,6 @@ import json
 import os
 import subprocess
 import sys
-import tempfile
 import time
 
 import numpy as np
@@ -73,43 +72,54 @@ def weak_scaled(case, world):
 
 
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons DURING the timed region (NVML polled from a thread every ~2 ms;
+    nvidia-smi's 100 ms loop is too coarse for a timed region of a few milliseconds)."""
 
     def __init__(self, gpu_index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        import threading
+        self.samples, self.reasons, self.ok = [], set(), False
+        self._stop = threading.Event()
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
-        except Exception:
-            self.p = None
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as exc:  # no NVML: report nulls, never fail the bench
+            self.err = repr(exc)
+            return
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        nv = self.nv
+        names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksEventReasonHwPowerBrakeSlowdown: "hw_power_brake_slowdown"}
+        while not self._stop.is_set():
+            try:
+                self.samples.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)),
+                                     nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
+        if not self.ok:
             return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        rows = [r.split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
-        os.unlink(self.f.name)
-        sm, mx, reasons = [], [], set()
-        for r in rows:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.strip().lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                continue
-        if sm:
-            busy = [s for s in sm if s > 0.5 * max(mx)] or sm
-            out.update(sm_mhz=float(np.median(busy)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        self._stop.set()
+        self.t.join(timeout=2)
+        if self.samples:
+            sm = [x[0] for x in self.samples]
+            out.update(sm_mhz=float(np.median(sm)), sm_min_mhz=float(min(sm)), sm_max_mhz=self.max_mhz,
+                       power_w_max=float(max(x[1] for x in self.samples)), reasons=sorted(self.reasons), samples=len(sm))
         return out
 
 
@@ -284,8 +294,9 @@ def main():
     for s, e in ev:
         flush.zero_()            # write 256 MB > L2: the next sweep re-reads J_next from HBM
         s.record()
-        eng.sweep(1)             # one Bellman sweep (+ all-gather of J for N>1); blocking on its own stats copy
-        e.record()
+        eng.sweep_nowait()       # one Bellman sweep incl. the fused dJ statistics (+ halo exchange for N>1), enqueued
+        e.record()               # asynchronously: the host never waits inside the timed region
+    last_stats = eng.collect_stats()  # the K statistics triples (one small D2H; all-reduced over ranks for N>1)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     step_ms = np.array([s.elapsed_time(e) for s, e in ev])
@@ -328,29 +339,48 @@ def main():
     # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region ----
     e2e = None
     if not args.no_e2e:
+        # every rank holds the full host J (the reference API's array) but uploads only the planes it
+        # keeps (slab + halo) and reads back only its own slab of J and pi
+        slab_n = kernel_eng.slab_nodes
         J_host = torch.empty(N, dtype=torch.float64).pin_memory()
-        pi_host = torch.empty(N, dtype=torch.int64).pin_memory()
-        J_host.copy_(torch.from_numpy(eng.get_J()))
-        J_np, pi_np = J_host.numpy(), pi_host.numpy()
+        Js_host = torch.empty(slab_n, dtype=torch.float64).pin_memory()
+        pis_host = torch.empty(slab_n, dtype=torch.int64).pin_memory()
+        J_host.zero_()
+        J_np, Js_np, pis_np = J_host.numpy(), Js_host.numpy(), pis_host.numpy()
+        kernel_eng.get_J(Js_np)
+        lo = kernel_eng.slab_begin * kernel_eng.plane
+        J_np[lo:lo + slab_n] = Js_np
+        if world > 1:  # complete the host copy once (not timed) so every rank uploads real halo data
+            t = torch.from_numpy(J_np).cuda()
+            dist.all_reduce(t)
+            J_host.copy_(t.cpu())
+        held = (kernel_eng.alloc_end - kernel_eng.alloc_begin) * kernel_eng.plane
         n_e2e = max(3, min(args.steps, 10))
+
+        def e2e_step():
+            eng.set_J(J_np)             # H2D: J_next planes this rank holds
+            eng.sweep(1)                # sweep (+ halo exchange and stats all-reduce for N>1)
+            kernel_eng.get_J(Js_np)     # D2H: J of the slab
+            kernel_eng.get_pi(pis_np)   # D2H: pi of the slab
         for _ in range(2):
-            eng.set_J(J_np); eng.sweep(1); eng.get_J(J_np); eng.get_pi(pi_np)
+            e2e_step()
         barrier()
         t0 = time.perf_counter()
         for _ in range(n_e2e):
-            eng.set_J(J_np)        # H2D: J_next, N doubles
-            eng.sweep(1)
-            eng.get_J(J_np)        # D2H: J, N doubles
-            eng.get_pi(pi_np)      # D2H: pi, N int64
+            e2e_step()
         barrier()
         dt = time.perf_counter() - t0
+        h2d, d2h = 8.0 * held, 16.0 * slab_n
         if world > 1:
-            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": evals_per_step * n_e2e / dt, "unit": "evals/s", "h2d_bytes_per_step": 8 * N * world,
-               "d2h_bytes_per_step": 16 * N * world, "steps": n_e2e, "ms_per_step": 1e3 * dt / n_e2e,
-               "call": "pdp_set_J + pdp_sweep(1) + pdp_get_J + pdp_get_pi, pinned host buffers"}
+            t = torch.tensor([dt, -dt, h2d, d2h], device="cuda", dtype=torch.float64)
+            mx = t.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            dt, h2d, d2h = float(mx[0].item()), float(t[2].item()), float(t[3].item())
+        e2e = {"value": evals_per_step * n_e2e / dt, "unit": "evals/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": n_e2e, "ms_per_step": 1e3 * dt / n_e2e,
+               "call": "pdp_set_J + pdp_sweep(1) + pdp_get_J + pdp_get_pi, pinned host buffers"
+                       + (" (per rank: its planes up, its slab down; halo exchange inside)" if world > 1 else "")}
 
     # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------------------------------
     cpu = cpu_nat = None
@@ -372,11 +402,13 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl_name, "system": case["system"], "x_grid_dim": case["x_grid_dim"],
                        "u_grid_dim": case["u_grid_dim"], "dt": case["dt"], "alpha": 1.0, "nodes": N, "actions": A,
-                       "evals_per_step": evals_per_step, "parallelism": f"slab{world}" if world > 1 else "single",
+                       "evals_per_step": evals_per_step,
+                       "parallelism": (f"slab{world}/{eng.mode}" + ("+overlap" if eng.overlap else "")) if world > 1 else "single",
                        "l2": f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)", "J0": "h(x) then warm-up sweeps"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu, "cpu_baseline_native": cpu_nat,
             "wall_s_timed_region": t_wall, "step_ms_min_max": [float(step_ms.min()), float(step_ms.max())],
+            "last_sweep_stats": {"j_max": float(last_stats[-1][0]), "delta_max": float(last_stats[-1][1]), "delta_min": float(last_stats[-1][2])},
             "J_Linf_error": "see tests/test_parity_gpu.py (bit-exact vs reference goldens)",
         }
         print(json.dumps(line), flush=True)

@@ -80,8 +80,10 @@ typedef struct pdp_problem {
     int32_t ontarget_check; /* costfunction.py:134 */
     int32_t slab_begin;  /* axis-0 planes [slab_begin, slab_end) are computed by this handle;   */
     int32_t slab_end;    /* 0, dims[0] on a single GPU (multi-GPU: SURVEY.md 8e)                  */
-    int32_t alloc_planes; /* axis-0 planes to allocate for the J buffers; 0 = dims[0].  A multi-GPU
-                             host sets W*ceil(dims[0]/W) so an equal-count in-place all-gather fits */
+    int32_t alloc_planes; /* 0: the handle holds its slab plus the halo its backups can read (the whole
+                             grid when the slab is the whole grid, or in LUT mode).  > 0: it holds the
+                             whole grid in buffers of alloc_planes planes, e.g. W*ceil(dims[0]/W), so an
+                             equal-count in-place all-gather of whole slabs fits (fallback exchange)  */
     int32_t reserved0;
     int32_t dims[PDP_MAX_N];  /* x_grid_dim (discretizer.py:91)  */
     int32_t udims[PDP_MAX_M]; /* u_grid_dim (discretizer.py:92)  */
@@ -122,21 +124,30 @@ const char* pdp_last_error(const pdp_handle* h);
 int pdp_set_stream(pdp_handle* h, void* cuda_stream);
 
 /* ---- cost-to-go state ---------------------------------------------------------------------
- * J is the latest cost-to-go (N doubles), pi the latest policy (N int64), J_next the previous J
- * (dynamicprogramming.py:181-185).  */
+ * J is the latest cost-to-go, pi the latest policy (int64), J_next the previous J
+ * (dynamicprogramming.py:181-185).  The getters return THE HANDLE'S SLAB: (slab_end-slab_begin) *
+ * prod(dims[1:]) values starting at plane slab_begin — on a single GPU that is the reference's
+ * (N,) array.  pdp_set_J always takes the full (N,) array and keeps the planes the handle holds. */
 /* replaces DynamicProgramming.evaluate_terminal_cost (dynamicprogramming.py:159-171): J = h(x, tf), pi = 0, on device */
 int pdp_eval_terminal_cost(pdp_handle* h);
 /* upload a full J (N doubles, host), e.g. terminal cost computed by the caller or load_J_next (:489-499) */
 int pdp_set_J(pdp_handle* h, const double* J_host);
-int pdp_get_J(pdp_handle* h, double* J_host);       /* N doubles  */
-int pdp_get_J_next(pdp_handle* h, double* J_host);  /* N doubles  */
-int pdp_get_pi(pdp_handle* h, int64_t* pi_host);    /* N int64    */
+int pdp_get_J(pdp_handle* h, double* J_host);       /* slab doubles  */
+int pdp_get_J_next(pdp_handle* h, double* J_host);  /* slab doubles  */
+int pdp_get_pi(pdp_handle* h, int64_t* pi_host);    /* slab int64    */
 
 /* ---- the hot path ---------------------------------------------------------------------------
  * replaces initialize_backward_step + compute_backward_step + the reductions of
  * finalize_backward_step (dynamicprogramming.py:175-261), n_sweeps times back to back on the
  * device.  stats_out (host, may be NULL) receives n_sweeps entries.  Blocking. */
 int pdp_sweep(pdp_handle* h, int32_t n_sweeps, pdp_stats* stats_out);
+
+/* The same, split in two for callers that must not block between sweeps (benchmarks, pipelines):
+ * pdp_sweep_enqueue queues one sweep (and, with a communicator attached, its halo exchange) on the
+ * handle's stream; pdp_sweep_collect waits, all-reduces the statistics over the ranks and returns
+ * the triples of the sweeps enqueued since the last collect (oldest first, at most max_out). */
+int pdp_sweep_enqueue(pdp_handle* h);
+int pdp_sweep_collect(pdp_handle* h, pdp_stats* stats_out, int32_t max_out, int32_t* n_out);
 
 /* LUT mode (system_id == PDP_SYS_LUT): the generic, bit-exact path for arbitrary user systems.
  * x_next: (N_slab, A, n) float64 as discretizer.py:349, G: (N_slab, A) float64 as
@@ -145,19 +156,42 @@ int pdp_sweep(pdp_handle* h, int32_t n_sweeps, pdp_stats* stats_out);
 int pdp_set_lut(pdp_handle* h, const double* x_next_host, const double* G_host);
 
 /* ---- step after the sweep: policy -> input tables (discretizer.py:616-633 get_input_from_policy),
- * u_k[s] = input_from_action_id[pi[s], k], computed on the device, N doubles to host */
+ * u_k[s] = input_from_action_id[pi[s], k], computed on the device, slab doubles to host */
 int pdp_get_input_from_policy(pdp_handle* h, int32_t k, double* uk_host);
 /* clean_infeasible_set (dynamicprogramming.py:322-334) on the device */
 int pdp_clean_infeasible_set(pdp_handle* h, double tol, int64_t default_action);
 
 /* ---- multi-GPU plumbing (one process per GPU; the host layer does the exchange) -------------
- * One asynchronous sweep of this handle's slab on its stream, no host sync.  The new J of the
- * slab is written in place into the full-size "new" buffer; the caller then all-gathers that
- * buffer across ranks (NCCL) and calls pdp_commit_sweep() to swap J/J_next. */
+ * One asynchronous sweep of this handle's slab on its stream, no host sync.  The new J of the slab
+ * is written into the "new" buffer; the caller then exchanges the halo planes of that buffer with
+ * the neighbouring ranks (NCCL send/recv, or an all-gather of whole slabs) and calls
+ * pdp_commit_sweep() to swap J/J_next.  pdp_sweep_planes_async does the same for a sub-range of the
+ * slab's planes (boundary planes first, so their exchange overlaps the interior); each concurrent
+ * range uses its own stat_set in 0..3 and writes its statistics triple to stats[3*stat_set]. */
+/* Native exchange: attach an NCCL communicator (libnccl.so.2 through dlopen — the copy the process
+ * already loaded, e.g. torch's) and pdp_sweep / pdp_sweep_enqueue run slab sweep + exchange +
+ * statistics all-reduce themselves: boundary planes first, grouped ncclSend/ncclRecv with ranks
+ * r-1 / r+1 on a side stream under the interior planes (exchange_mode 1), or an in-place
+ * ncclAllGather of whole slabs (exchange_mode 2).  id128 = the 128-byte ncclUniqueId made by
+ * pdp_nccl_unique_id on rank 0 and distributed by the caller. */
+int pdp_nccl_unique_id(void* id128);
+int pdp_comm_init(pdp_handle* h, int32_t rank, int32_t world, const void* id128, int32_t exchange_mode, int32_t overlap);
+int pdp_exchange_current(pdp_handle* h);
+/* Caller-driven exchange (any transport): */
 int pdp_sweep_async(pdp_handle* h);
+int pdp_sweep_planes_async(pdp_handle* h, int32_t plane_begin, int32_t plane_end, int32_t stat_set);
 int pdp_commit_sweep(pdp_handle* h);
-/* device pointers: J (N_pad doubles, current), J_new (N_pad doubles, being written), pi (N int64),
- * stats (3 doubles of the last async sweep: j_max, delta_max, delta_min over the slab) */
+/* wait for the handle's stream and copy the four statistics triples (12 doubles) to the host */
+int pdp_read_stats(pdp_handle* h, double* stats_host);
+/* layout[8] = {slab_begin, slab_end, alloc_begin, alloc_end, halo_lo, halo_hi, dims[0], lanes_per_node}:
+ * the J buffers hold planes [alloc_begin, alloc_end); a backup of plane i reads planes
+ * [i - halo_lo, i + halo_hi] at most (computed from the levels, dt and bounds at pdp_create). */
+int pdp_slab_layout(const pdp_handle* h, int32_t layout[8]);
+/* the halo alone, from the descriptor (host arithmetic only, needs no device) */
+int pdp_compute_halo(const pdp_problem* p, int32_t* halo_lo, int32_t* halo_hi);
+/* device pointers: J (current) and J_new (being written), element 0 = first node of plane alloc_begin,
+ * pdp_nodes_padded() doubles each; pi (slab int64, element 0 = first node of plane slab_begin);
+ * stats (4 triples {j_max, delta_max, delta_min}, one per stat_set, of the last async launches) */
 int pdp_device_buffers(pdp_handle* h, void** J_cur, void** J_new, void** pi, void** stats);
 int64_t pdp_nodes(const pdp_handle* h);        /* N = prod(dims) */
 int64_t pdp_nodes_padded(const pdp_handle* h); /* N_pad: allocation size of the J buffers */

@@ -53,11 +53,20 @@ SIGNATURES = {
     "pdp_get_J_next": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pdp_get_pi": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pdp_sweep": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "pdp_sweep_enqueue": (C.c_int, [C.c_void_p]),
+    "pdp_sweep_collect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
+    "pdp_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "pdp_comm_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32]),
+    "pdp_exchange_current": (C.c_int, [C.c_void_p]),
     "pdp_set_lut": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pdp_get_input_from_policy": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "pdp_clean_infeasible_set": (C.c_int, [C.c_void_p, C.c_double, C.c_int64]),
     "pdp_sweep_async": (C.c_int, [C.c_void_p]),
+    "pdp_sweep_planes_async": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
     "pdp_commit_sweep": (C.c_int, [C.c_void_p]),
+    "pdp_read_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pdp_slab_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "pdp_compute_halo": (C.c_int, [C.POINTER(pdp_problem), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "pdp_device_buffers": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_void_p)] * 4),
     "pdp_nodes": (C.c_int64, [C.c_void_p]),
     "pdp_nodes_padded": (C.c_int64, [C.c_void_p]),

@@ -10,9 +10,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <dlfcn.h>
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -77,8 +79,8 @@ sweep_lut_kernel(const __grid_constant__ DevProblem P, const double* __restrict_
                  long long* __restrict__ pi, const double* __restrict__ xnext, const double* __restrict__ Gtab,
                  unsigned long long* __restrict__ partials, unsigned int* counter, double* __restrict__ stats) {
     const int lane_in_group = threadIdx.x % G;
-    const long long slot = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;  // node within slab
-    const long long node = P.node_begin + slot;
+    const long long node = P.node_begin + ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const long long slot = node - P.slab_node_begin;  // row of the (slab-local) x_next / G tables
     const int A = P.A;
     Stats3 st = stats_identity();
     const bool active = node < P.node_end;
@@ -109,9 +111,11 @@ sweep_lut_kernel(const __grid_constant__ DevProblem P, const double* __restrict_
 
 // ---- terminal cost (dynamicprogramming.py:159-171) -------------------------------------------------
 template <int N>
-__global__ void terminal_cost_kernel(const __grid_constant__ DevProblem P, double* __restrict__ J, long long* __restrict__ pi) {
-    const long long node = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (node >= P.N) return;
+__global__ void terminal_cost_kernel(const __grid_constant__ DevProblem P, double* __restrict__ J, long long* __restrict__ pi,
+                                     long long first, long long last) {
+    // J and pi are virtual bases indexed by global node id; [first,last) = allocated planes (slab + halo)
+    const long long node = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= last) return;
     double dx[N];
     long long r = node;
 #pragma unroll
@@ -127,11 +131,6 @@ __global__ void terminal_cost_kernel(const __grid_constant__ DevProblem P, doubl
     }
     J[node] = h;
     if (node >= P.node_begin && node < P.node_end) pi[node] = 0;
-}
-
-__global__ void fill_pi_kernel(long long* pi, long long n) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) pi[i] = 0;
 }
 
 // ---- after the sweep: pi -> u_k table (discretizer.py:616-633), infeasible-set cleaning (:322-334) ----
@@ -159,22 +158,45 @@ __global__ void exact_div_test_kernel(const double* a, const double* den, double
     }
 }
 
+// ---- statistics plumbing for range launches / ranks ------------------------------------------------
+// fold `nsets` triples {jmax, dmax, dmin} into dst = {jmax, dmax, -dmin} (all-reduce with MAX), and back
+__global__ void stats_fold_kernel(const double* __restrict__ sets, int nsets, double* __restrict__ dst) {
+    double a = sets[0], b = sets[1], c = sets[2];
+    for (int i = 1; i < nsets; ++i) {
+        a = fmax(a, sets[3 * i]); b = fmax(b, sets[3 * i + 1]); c = fmin(c, sets[3 * i + 2]);
+    }
+    dst[0] = a; dst[1] = b; dst[2] = -c;
+}
+__global__ void stats_unfold_kernel(double* __restrict__ st, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) st[3 * i + 2] = -st[3 * i + 2];
+}
+
 // =================================================================================================
 // Host side: handle + C ABI
 // =================================================================================================
 
+#define PDP_STAT_SETS 4  // independent stats scratch sets, so range launches may overlap on different streams
+
 struct pdp_handle {
     DevProblem P{};
     int device = 0;
-    long long N = 0, N_pad = 0, plane = 0;
+    long long N = 0, plane = 0;   // nodes of the whole grid, nodes per axis-0 plane
     int A = 0;
-    double* dJ[2] = {nullptr, nullptr};  // cur = dJ[cur_idx], new = dJ[1-cur_idx]
+    int n0 = 0;                   // dims[0]
+    int slab_begin = 0, slab_end = 0;    // planes computed by this handle
+    int alloc_begin = 0, alloc_end = 0;  // planes held in the J buffers (slab + halo, or everything)
+    int halo_lo = 0, halo_hi = 0;        // planes below / above a node that its backup can read
+    long long alloc_planes_cap = 0;      // planes allocated (>= alloc_end - alloc_begin; padded all-gather layout)
+    double* dJ[2] = {nullptr, nullptr};  // cur = dJ[cur_idx], new = dJ[1-cur_idx]; element 0 = plane alloc_begin
     int cur_idx = 0;
-    long long* dpi = nullptr;
-    double* dstats = nullptr;     // [stats_cap][3]
+    long long* dpi = nullptr;     // slab planes only; element 0 = plane slab_begin
+    double* dstats = nullptr;     // [stats_cap][3] history of enqueued sweeps (pdp_sweep / pdp_sweep_enqueue)
     int stats_cap = 0;
-    unsigned long long* dpartials = nullptr;  // [STATS_SLOTS][3] order-preserving keys (block_stats_finish)
-    unsigned int* dcounter = nullptr;
+    int enqueued = 0;             // sweeps enqueued since the last collect
+    double* dstats_sets = nullptr;  // [PDP_STAT_SETS][3] triples of the range launches
+    unsigned long long* dslots = nullptr;  // [PDP_STAT_SETS][STATS_SLOTS][3] order-preserving keys
+    unsigned int* dcounter = nullptr;      // [PDP_STAT_SETS]
     std::vector<void*> owned;     // small device tables
     double* d_xnext = nullptr;
     double* d_G = nullptr;
@@ -190,10 +212,41 @@ struct pdp_handle {
     int lanes_per_node = 1;       // G of the fused kernels
     int force_lanes = 0;          // test hook (PYRODP_LANES): pin G to 1, 4 or 16
     void* fused = nullptr;        // selected fused kernel instantiation
-    dim3 grid{1, 1, 1};
+    // multi-GPU (one process per GPU): NCCL communicator, side stream for the halo exchange
+    void* comm = nullptr;
+    int rank = 0, world = 1;
+    int exchange_mode = 0;        // 0 none, 1 halo send/recv with ranks r-1 / r+1, 2 in-place all-gather of whole slabs
+    int overlap = 1;              // boundary planes first, exchange under the interior planes
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_boundary = nullptr, ev_comm = nullptr;
+    long long exchanges = 0;
+
+    long long slab_nodes() const { return (long long)(slab_end - slab_begin) * plane; }
+    long long alloc_nodes() const { return (long long)(alloc_end - alloc_begin) * plane; }
+    // virtual bases: index with the global node id
+    double* Jv(int which) const { return dJ[which] - (long long)alloc_begin * plane; }
+    long long* piv() const { return dpi - (long long)slab_begin * plane; }
 };
 
 static thread_local std::string g_err;
+
+// NCCL entry points, resolved at run time (see nccl_load)
+typedef struct { char internal[128]; } pdp_nccl_id;
+static struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(pdp_nccl_id*) = nullptr;
+    int (*CommInitRank)(void**, int, pdp_nccl_id, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+} g_nccl;
+enum { PDP_NCCL_F64 = 8, PDP_NCCL_MAX = 2 };  // ncclFloat64, ncclMax (nccl.h)
+
 
 static int fail(pdp_handle* h, int code, const std::string& msg) {
     if (h) {
@@ -255,9 +308,9 @@ static fused_kernel_t fused_for(int system_id) {
 
 // G lanes per node: 1 when the slab alone fills the GPU, else 4 or 16 so that small grids still
 // spread over the 148 SMs (the shuffle argmin keeps np.argmin's first-index rule).
-static int select_fused_kernel(pdp_handle* h, const pdp_problem* p) {
+static int select_fused_kernel(pdp_handle* h) {
     DevProblem& P = h->P;
-    const long long slab_nodes = P.node_end - P.node_begin;
+    const long long slab_nodes = h->slab_nodes();
     int sm_count = 148;
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
     const long long want_threads = (long long)sm_count * 2048;  // one full wave of resident threads
@@ -277,23 +330,50 @@ static int select_fused_kernel(pdp_handle* h, const pdp_problem* p) {
     if (P.system_id == PDP_SYS_PENDULUM) {
         const size_t n1p = (size_t)((P.dims[1] + 1) & ~1);
         h->smem_bytes = (2 * n1p + 2 * A) * sizeof(double) + 16;
-        const long long threads = slab_nodes * G;
-        const long long blocks = (threads + SWEEP_THREADS - 1) / SWEEP_THREADS;
-        if (blocks > 0x7fffffffLL) return fail(h, PDP_ENOTSUP, "grid too large for one launch");
-        h->grid = dim3((unsigned)(blocks > 0 ? blocks : 1), 1, 1);
+        if (h->N > 0x7fffffffLL) return fail(h, PDP_ENOTSUP, "2-D grids are limited to 2^31-1 nodes");
     } else {
         const size_t n2p = (size_t)((P.dims[2] + 1) & ~1), n3p = (size_t)((P.dims[3] + 1) & ~1);
         h->smem_bytes = (2 * n2p + 2 * n3p + 4 * A) * sizeof(double) + 16;
         const long long plane_sz = (long long)P.dims[2] * P.dims[3];
         const long long chunks = (plane_sz * G + SWEEP_THREADS - 1) / SWEEP_THREADS;
-        const long long planes = (long long)(p->slab_end - p->slab_begin) * P.dims[1];
-        if (plane_sz > 0x7fffffffLL / 16 || chunks > 65535 || planes > 0x7fffffffLL)
+        if (plane_sz > 0x7fffffffLL / 16 || chunks > 65535)
             return fail(h, PDP_ENOTSUP, "grid too large for one launch (dims[2]*dims[3] too big)");
-        h->grid = dim3((unsigned)(planes > 0 ? planes : 1), (unsigned)chunks, 1);
     }
     if (h->smem_bytes > 227 * 1024) return fail(h, PDP_ENOTSUP, "level/action tables exceed shared memory (227 KB)");
     cudaError_t ce = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
     if (ce != cudaSuccess) return fail(h, PDP_ECUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
+    return PDP_OK;
+}
+
+// Halo of the axis-0 slab decomposition: how many planes below / above its own plane a node's
+// backup can read.  Axis 0 is a position (MechanicalSystem: x = [q, dq], mechanical.py:238-263), so
+// x_next[0] = dq0*dt + q0 depends on (i0, index of dq0) only: enumerate those pairs with the same two
+// IEEE operations the kernels use and let the level table decide the cell, exactly as they do.
+static void compute_halo(const pdp_problem* p, int* halo_lo, int* halo_hi) {
+    const int n0 = p->dims[0], vax = p->n / 2, nv = p->dims[vax];
+    const double* lev0 = p->x_level[0];
+    const double* levv = p->x_level[vax];
+    int lo = 0, hi = 1;
+    for (int i0 = 0; i0 < n0; ++i0)
+        for (int iv = 0; iv < nv; ++iv) {
+            volatile double prod = levv[iv] * p->dt;   // volatile: two roundings, never an fma
+            const double xn0 = prod + lev0[i0];
+            if (xn0 < p->x_lb[0] || xn0 > p->x_ub[0]) continue;
+            int c = (int)(std::upper_bound(lev0, lev0 + n0, xn0) - lev0) - 1;
+            c = std::min(std::max(c, 0), n0 - 2);
+            lo = std::max(lo, i0 - c);
+            hi = std::max(hi, c + 1 - i0);
+        }
+    *halo_lo = lo;
+    *halo_hi = hi;
+}
+
+extern "C" int pdp_compute_halo(const pdp_problem* p, int32_t* halo_lo, int32_t* halo_hi) {
+    if (!p || !halo_lo || !halo_hi) return fail(nullptr, PDP_EINVAL, "pdp_compute_halo: null argument");
+    if (p->n < 2 || p->n > 4 || p->system_id == PDP_SYS_LUT) { *halo_lo = *halo_hi = p->dims[0]; return PDP_OK; }
+    int lo, hi;
+    compute_halo(p, &lo, &hi);
+    *halo_lo = lo; *halo_hi = hi;
     return PDP_OK;
 }
 
@@ -334,6 +414,13 @@ extern "C" int pdp_create(const pdp_problem* p, pdp_handle** out) {
         if (want && (!p->sys_tab[t] || p->sys_tab_len[t] != want))
             return fail(nullptr, PDP_EINVAL, "pdp_create: sys_tab[" + std::to_string(t) + "] has wrong length");
     }
+    for (int d = 0; d < p->n; ++d) {
+        if (p->x_level[d][0] != p->x_lb[d] || p->x_level[d][p->dims[d] - 1] != p->x_ub[d])
+            return fail(nullptr, PDP_EINVAL, "pdp_create: x_level end points must equal x_lb/x_ub (np.linspace, discretizer.py:142)");
+        for (int i = 0; i + 1 < p->dims[d]; ++i)
+            if (!(p->x_level[d][i + 1] - p->x_level[d][i] > 0.0))
+                return fail(nullptr, PDP_EINVAL, "pdp_create: x_level must be strictly increasing");
+    }
 
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -344,6 +431,7 @@ extern "C" int pdp_create(const pdp_problem* p, pdp_handle** out) {
     pdp_handle* h = new pdp_handle();
     auto bail = [&](int code) { pdp_destroy(h); return code; };
     if (cudaGetDevice(&h->device) != cudaSuccess) { g_err = "cudaGetDevice failed"; return bail(PDP_ECUDA); }
+    if (const char* env = getenv("PYRODP_LANES")) h->force_lanes = atoi(env);
 
     DevProblem& P = h->P;
     P.n = p->n; P.m = p->m; P.dof = p->n / 2; P.A = (int)A;
@@ -353,34 +441,40 @@ extern "C" int pdp_create(const pdp_problem* p, pdp_handle** out) {
     long long stride = 1;
     for (int d = p->n - 1; d >= 0; --d) { P.stride[d] = stride; stride *= p->dims[d]; }
     h->N = N; h->A = (int)A; P.N = N;
+    h->n0 = p->dims[0];
     h->plane = N / p->dims[0];
-    // J buffers may be padded (alloc_planes) so an in-place equal-count all-gather fits
-    long long pad_planes = p->alloc_planes > 0 ? p->alloc_planes : p->dims[0];
-    if (pad_planes < p->dims[0]) { g_err = "pdp_create: alloc_planes < dims[0]"; return bail(PDP_EINVAL); }
-    h->N_pad = pad_planes * h->plane;
+    h->slab_begin = p->slab_begin; h->slab_end = p->slab_end;
+
+    // ---- which planes of J this handle holds ---------------------------------------------------
+    //  * whole grid on one GPU: everything.
+    //  * a slab, alloc_planes == 0: slab + halo (fused systems), the 180 GB-per-GPU layout;
+    //    LUT mode keeps everything (an arbitrary x_next_table has no a-priori halo).
+    //  * a slab, alloc_planes > 0: everything, padded to alloc_planes planes so that an in-place
+    //    equal-count all-gather of whole slabs fits (used when the halo exceeds a neighbour's slab).
+    const bool partial = (p->slab_begin != 0 || p->slab_end != p->dims[0]);
+    h->halo_lo = h->halo_hi = p->dims[0];
+    if (p->system_id != PDP_SYS_LUT) compute_halo(p, &h->halo_lo, &h->halo_hi);
+    if (!partial || p->alloc_planes > 0 || p->system_id == PDP_SYS_LUT) {
+        h->alloc_begin = 0; h->alloc_end = p->dims[0];
+        h->alloc_planes_cap = p->alloc_planes > 0 ? p->alloc_planes : p->dims[0];
+        if (h->alloc_planes_cap < p->dims[0]) { g_err = "pdp_create: alloc_planes < dims[0]"; return bail(PDP_EINVAL); }
+    } else {
+        h->alloc_begin = std::max(0, p->slab_begin - h->halo_lo);
+        h->alloc_end = std::min((int)p->dims[0], p->slab_end + h->halo_hi);
+        h->alloc_planes_cap = h->alloc_end - h->alloc_begin;
+    }
     P.node_begin = (long long)p->slab_begin * h->plane;
     P.node_end = (long long)p->slab_end * h->plane;
-    P.plane_begin = (long long)p->slab_begin * (p->n >= 2 ? p->dims[1] : 1);
-    P.all_act_ok = 1;
-    if (p->system_id != PDP_SYS_LUT)
-        for (long long a = 0; a < A; ++a) if (!p->act_ok[a]) P.all_act_ok = 0;
-    if (const char* env = getenv("PYRODP_LANES")) h->force_lanes = atoi(env);
+    P.slab_node_begin = P.node_begin;
+    P.plane_begin = (long long)p->slab_begin * p->dims[1];
 
     int rc;
     for (int d = 0; d < p->n; ++d) {
         P.dims[d] = p->dims[d];
         P.lb[d] = p->x_lb[d]; P.ub[d] = p->x_ub[d];
         P.inv_step[d] = (double)(p->dims[d] - 1) / (p->x_ub[d] - p->x_lb[d]);
-        if (p->x_level[d][0] != p->x_lb[d] || p->x_level[d][p->dims[d] - 1] != p->x_ub[d]) {
-            g_err = "pdp_create: x_level end points must equal x_lb/x_ub (np.linspace, discretizer.py:142)";
-            return bail(PDP_EINVAL);
-        }
         std::vector<double> rinv(p->dims[d]);
-        for (int i = 0; i + 1 < p->dims[d]; ++i) {
-            const double den = p->x_level[d][i + 1] - p->x_level[d][i];
-            if (!(den > 0.0)) { g_err = "pdp_create: x_level must be strictly increasing"; return bail(PDP_EINVAL); }
-            rinv[i] = 1.0 / den;
-        }
+        for (int i = 0; i + 1 < p->dims[d]; ++i) rinv[i] = 1.0 / (p->x_level[d][i + 1] - p->x_level[d][i]);
         rinv[p->dims[d] - 1] = 0.0;
         if ((rc = upload(h, p->x_level[d], p->dims[d], &P.level[d])) != PDP_OK) return bail(rc);
         if ((rc = upload(h, rinv.data(), rinv.size(), &P.rinv[d])) != PDP_OK) return bail(rc);
@@ -400,12 +494,16 @@ extern "C" int pdp_create(const pdp_problem* p, pdp_handle** out) {
         }
         if ((rc = upload(h, u_flat.data(), u_flat.size(), &P.u_flat)) != PDP_OK) return bail(rc);
     }
+    P.all_act_ok = 1;
     if (p->system_id != PDP_SYS_LUT) {
         // isavalidinput (system.py:208-215) is folded into the B.u table: a disallowed action carries
         // NaN, its x_next is NaN, fails the box test and gets Q = INF exactly as dynamicprogramming.py:233
         std::vector<double> bu(p->bu, p->bu + (size_t)A * P.dof);
         for (long long a = 0; a < A; ++a)
-            if (!p->act_ok[a]) for (int d = 0; d < P.dof; ++d) bu[(size_t)a * P.dof + d] = __builtin_nan("");
+            if (!p->act_ok[a]) {
+                P.all_act_ok = 0;
+                for (int d = 0; d < P.dof; ++d) bu[(size_t)a * P.dof + d] = __builtin_nan("");
+            }
         if ((rc = upload(h, bu.data(), bu.size(), &P.bu)) != PDP_OK) return bail(rc);
         if ((rc = upload(h, p->gu, (size_t)A, &P.gu)) != PDP_OK) return bail(rc);
         if ((rc = upload(h, (const unsigned char*)p->act_ok, (size_t)A, &P.act_ok)) != PDP_OK) return bail(rc);
@@ -415,24 +513,28 @@ extern "C" int pdp_create(const pdp_problem* p, pdp_handle** out) {
         if (ce != cudaSuccess) { g_err = std::string(what) + ": " + cudaGetErrorString(ce); return false; }
         return true;
     };
-    if (!cu(cudaMalloc(&h->dJ[0], h->N_pad * sizeof(double)), "cudaMalloc J0")) return bail(PDP_ECUDA);
-    if (!cu(cudaMalloc(&h->dJ[1], h->N_pad * sizeof(double)), "cudaMalloc J1")) return bail(PDP_ECUDA);
-    if (!cu(cudaMalloc(&h->dpi, h->N * sizeof(long long)), "cudaMalloc pi")) return bail(PDP_ECUDA);
+    const size_t jbytes = (size_t)std::max<long long>(h->alloc_planes_cap * h->plane, 1) * sizeof(double);
+    const size_t pibytes = (size_t)std::max<long long>(h->slab_nodes(), 1) * sizeof(long long);
+    if (!cu(cudaMalloc(&h->dJ[0], jbytes), "cudaMalloc J0")) return bail(PDP_ECUDA);
+    if (!cu(cudaMalloc(&h->dJ[1], jbytes), "cudaMalloc J1")) return bail(PDP_ECUDA);
+    if (!cu(cudaMalloc(&h->dpi, pibytes), "cudaMalloc pi")) return bail(PDP_ECUDA);
     h->stats_cap = 256;
     if (!cu(cudaMalloc(&h->dstats, h->stats_cap * 3 * sizeof(double)), "cudaMalloc stats")) return bail(PDP_ECUDA);
-    if (!cu(cudaMalloc(&h->dpartials, 3 * STATS_SLOTS * sizeof(unsigned long long)), "cudaMalloc stats slots")) return bail(PDP_ECUDA);
-    if (!cu(cudaMemset(h->dpartials, 0, 3 * STATS_SLOTS * sizeof(unsigned long long)), "cudaMemset stats slots")) return bail(PDP_ECUDA);
-    if (!cu(cudaMalloc(&h->dcounter, sizeof(unsigned int)), "cudaMalloc counter")) return bail(PDP_ECUDA);
-    if (!cu(cudaMemset(h->dcounter, 0, sizeof(unsigned int)), "cudaMemset counter")) return bail(PDP_ECUDA);
-    if (!cu(cudaMemset(h->dpi, 0, h->N * sizeof(long long)), "cudaMemset pi")) return bail(PDP_ECUDA);
+    if (!cu(cudaMalloc(&h->dstats_sets, PDP_STAT_SETS * 3 * sizeof(double)), "cudaMalloc stats sets")) return bail(PDP_ECUDA);
+    const size_t slot_bytes = (size_t)PDP_STAT_SETS * 3 * STATS_SLOTS * sizeof(unsigned long long);
+    if (!cu(cudaMalloc(&h->dslots, slot_bytes), "cudaMalloc stats slots")) return bail(PDP_ECUDA);
+    if (!cu(cudaMemset(h->dslots, 0, slot_bytes), "cudaMemset stats slots")) return bail(PDP_ECUDA);
+    if (!cu(cudaMalloc(&h->dcounter, PDP_STAT_SETS * sizeof(unsigned int)), "cudaMalloc counter")) return bail(PDP_ECUDA);
+    if (!cu(cudaMemset(h->dcounter, 0, PDP_STAT_SETS * sizeof(unsigned int)), "cudaMemset counter")) return bail(PDP_ECUDA);
+    if (!cu(cudaMemset(h->dpi, 0, pibytes), "cudaMemset pi")) return bail(PDP_ECUDA);
     if (!cu(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) return bail(PDP_ECUDA);
     h->own_stream = true;
     if (!cu(cudaEventCreate(&h->ev0), "cudaEventCreate")) return bail(PDP_ECUDA);
     if (!cu(cudaEventCreate(&h->ev1), "cudaEventCreate")) return bail(PDP_ECUDA);
 
-    // fused kernels: lanes per node, grid shape, kernel instantiation, dynamic shared memory
+    // fused kernels: lanes per node, kernel instantiation, dynamic shared memory
     if (p->system_id != PDP_SYS_LUT) {
-        int rcsel = select_fused_kernel(h, p);
+        int rcsel = select_fused_kernel(h);
         if (rcsel != PDP_OK) return bail(rcsel);
     }
     *out = h;
@@ -444,8 +546,12 @@ extern "C" int pdp_destroy(pdp_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (void* p : h->owned) cudaFree(p);
-    cudaFree(h->dJ[0]); cudaFree(h->dJ[1]); cudaFree(h->dpi); cudaFree(h->dstats);
-    cudaFree(h->dpartials); cudaFree(h->dcounter); cudaFree(h->d_xnext); cudaFree(h->d_G);
+    cudaFree(h->dJ[0]); cudaFree(h->dJ[1]); cudaFree(h->dpi); cudaFree(h->dstats); cudaFree(h->dstats_sets);
+    cudaFree(h->dslots); cudaFree(h->dcounter); cudaFree(h->d_xnext); cudaFree(h->d_G);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+    if (h->ev_boundary) cudaEventDestroy(h->ev_boundary);
+    if (h->ev_comm) cudaEventDestroy(h->ev_comm);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -472,64 +578,81 @@ extern "C" int pdp_set_stream(pdp_handle* h, void* cuda_stream) {
 }
 
 extern "C" int64_t pdp_nodes(const pdp_handle* h) { return h ? h->N : 0; }
-extern "C" int64_t pdp_nodes_padded(const pdp_handle* h) { return h ? h->N_pad : 0; }
+extern "C" int64_t pdp_nodes_padded(const pdp_handle* h) { return h ? h->alloc_planes_cap * h->plane : 0; }
 extern "C" int64_t pdp_actions(const pdp_handle* h) { return h ? h->A : 0; }
 extern "C" int64_t pdp_launch_count(const pdp_handle* h) { return h ? h->launches : 0; }
 extern "C" double pdp_last_sweep_ms(const pdp_handle* h) { return h ? h->last_ms : 0.0; }
+
+extern "C" int pdp_slab_layout(const pdp_handle* h, int32_t out[8]) {
+    if (!h || !out) return fail(nullptr, PDP_EINVAL, "pdp_slab_layout: null argument");
+    out[0] = h->slab_begin; out[1] = h->slab_end;
+    out[2] = h->alloc_begin; out[3] = h->alloc_end;
+    out[4] = h->halo_lo; out[5] = h->halo_hi;
+    out[6] = h->n0; out[7] = h->lanes_per_node;
+    return PDP_OK;
+}
 
 extern "C" int pdp_eval_terminal_cost(pdp_handle* h) {
     CHECK_HANDLE(h);
     if (h->P.system_id == PDP_SYS_LUT) return fail(h, PDP_ENOTSUP, "pdp_eval_terminal_cost: LUT mode has no cost model; use pdp_set_J");
     const int threads = 256;
-    const long long blocks = (h->N + threads - 1) / threads;
-    double* J = h->dJ[h->cur_idx];
-    if (h->P.n == 2) terminal_cost_kernel<2><<<(unsigned)blocks, threads, 0, h->stream>>>(h->P, J, h->dpi);
-    else if (h->P.n == 4) terminal_cost_kernel<4><<<(unsigned)blocks, threads, 0, h->stream>>>(h->P, J, h->dpi);
-    else return fail(h, PDP_ENOTSUP, "pdp_eval_terminal_cost: n must be 2 or 4");
-    CUDA_TRY(h, cudaGetLastError());
+    const long long first = (long long)h->alloc_begin * h->plane, last = (long long)h->alloc_end * h->plane;
+    const long long blocks = (last - first + threads - 1) / threads;
+    if (blocks > 0) {
+        double* J = h->Jv(h->cur_idx);
+        if (h->P.n == 2) terminal_cost_kernel<2><<<(unsigned)blocks, threads, 0, h->stream>>>(h->P, J, h->piv(), first, last);
+        else if (h->P.n == 4) terminal_cost_kernel<4><<<(unsigned)blocks, threads, 0, h->stream>>>(h->P, J, h->piv(), first, last);
+        else return fail(h, PDP_ENOTSUP, "pdp_eval_terminal_cost: n must be 2 or 4");
+        CUDA_TRY(h, cudaGetLastError());
+    }
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->have_J = true;
     return PDP_OK;
 }
 
+// J_host is always the FULL grid (N doubles); the handle copies the planes it holds.
 extern "C" int pdp_set_J(pdp_handle* h, const double* J_host) {
     CHECK_HANDLE(h);
     if (!J_host) return fail(h, PDP_EINVAL, "pdp_set_J: null pointer");
-    CUDA_TRY(h, cudaMemcpyAsync(h->dJ[h->cur_idx], J_host, h->N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (h->alloc_nodes() > 0)
+        CUDA_TRY(h, cudaMemcpyAsync(h->dJ[h->cur_idx], J_host + (long long)h->alloc_begin * h->plane,
+                                    h->alloc_nodes() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->have_J = true;
     return PDP_OK;
 }
 
 static int copy_out(pdp_handle* h, void* dst, const void* src, size_t bytes) {
-    CUDA_TRY(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (bytes) CUDA_TRY(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return PDP_OK;
 }
 
+// The getters return THIS HANDLE'S SLAB (slab_nodes values, plane slab_begin first); on a single
+// GPU the slab is the whole grid, i.e. the reference's (N,) arrays.
 extern "C" int pdp_get_J(pdp_handle* h, double* J_host) {
     CHECK_HANDLE(h);
     if (!J_host) return fail(h, PDP_EINVAL, "pdp_get_J: null pointer");
     if (!h->have_J) return fail(h, PDP_ESTATE, "pdp_get_J: no cost-to-go yet");
-    return copy_out(h, J_host, h->dJ[h->cur_idx], h->N * sizeof(double));
+    return copy_out(h, J_host, h->Jv(h->cur_idx) + h->P.slab_node_begin, h->slab_nodes() * sizeof(double));
 }
 extern "C" int pdp_get_J_next(pdp_handle* h, double* J_host) {
     CHECK_HANDLE(h);
     if (!J_host) return fail(h, PDP_EINVAL, "pdp_get_J_next: null pointer");
     if (!h->have_J) return fail(h, PDP_ESTATE, "pdp_get_J_next: no cost-to-go yet");
-    return copy_out(h, J_host, h->dJ[1 - h->cur_idx], h->N * sizeof(double));
+    return copy_out(h, J_host, h->Jv(1 - h->cur_idx) + h->P.slab_node_begin, h->slab_nodes() * sizeof(double));
 }
 extern "C" int pdp_get_pi(pdp_handle* h, int64_t* pi_host) {
     CHECK_HANDLE(h);
     if (!pi_host) return fail(h, PDP_EINVAL, "pdp_get_pi: null pointer");
-    return copy_out(h, pi_host, h->dpi, h->N * sizeof(long long));
+    return copy_out(h, pi_host, h->dpi, h->slab_nodes() * sizeof(long long));
 }
 
 extern "C" int pdp_set_lut(pdp_handle* h, const double* x_next_host, const double* G_host) {
     CHECK_HANDLE(h);
     if (h->P.system_id != PDP_SYS_LUT) return fail(h, PDP_ESTATE, "pdp_set_lut: handle was not created with PDP_SYS_LUT");
     if (!x_next_host || !G_host) return fail(h, PDP_EINVAL, "pdp_set_lut: null pointer");
-    const size_t slab = (size_t)(h->P.node_end - h->P.node_begin);
+    const size_t slab = (size_t)h->slab_nodes();
     const size_t nx = slab * h->A * h->P.n, ng = slab * h->A;
     if (!h->d_xnext) CUDA_TRY(h, cudaMalloc(&h->d_xnext, (nx ? nx : 1) * sizeof(double)));
     if (!h->d_G) CUDA_TRY(h, cudaMalloc(&h->d_G, (ng ? ng : 1) * sizeof(double)));
@@ -541,11 +664,12 @@ extern "C" int pdp_set_lut(pdp_handle* h, const double* x_next_host, const doubl
 }
 
 template <int N>
-static void launch_lut(pdp_handle* h, int G, unsigned blocks, const double* Jn, double* Jo, double* stats) {
+static void launch_lut(pdp_handle* h, cudaStream_t stream, const DevProblem& P, int G, unsigned blocks, const double* Jn, double* Jo,
+                       unsigned long long* slots, unsigned int* counter, double* stats) {
 #define LUT_CASE(g)                                                                                                  \
     case g:                                                                                                          \
-        sweep_lut_kernel<N, g><<<blocks, SWEEP_THREADS, 0, h->stream>>>(h->P, Jn, Jo, h->dpi, h->d_xnext, h->d_G,  \
-                                                                        h->dpartials, h->dcounter, stats);          \
+        sweep_lut_kernel<N, g><<<blocks, SWEEP_THREADS, 0, stream>>>(P, Jn, Jo, h->piv(), h->d_xnext, h->d_G,    \
+                                                                        slots, counter, stats);                     \
         break;
     switch (G) {
         LUT_CASE(1) LUT_CASE(2) LUT_CASE(4) LUT_CASE(8) LUT_CASE(16) LUT_CASE(32)
@@ -553,28 +677,45 @@ static void launch_lut(pdp_handle* h, int G, unsigned blocks, const double* Jn, 
 #undef LUT_CASE
 }
 
-// one sweep on the stream: reads dJ[cur], writes dJ[1-cur] (slab only), pi (slab), stats[3]
-static int launch_sweep(pdp_handle* h, double* stats) {
-    const DevProblem& P = h->P;
-    const long long slab_nodes = P.node_end - P.node_begin;
-    const double* Jn = h->dJ[h->cur_idx];
-    double* Jo = h->dJ[1 - h->cur_idx];
-    if (slab_nodes <= 0) {
+// One backup of axis-0 planes [p0,p1) (a sub-range of the slab) on the handle's stream:
+// reads J[cur] (slab + halo), writes J[1-cur] and pi on those planes, stats triple -> `stats`.
+static int launch_planes(pdp_handle* h, int p0, int p1, int stat_set, double* stats, cudaStream_t stream = nullptr) {
+    if (!stream) stream = h->stream;
+    DevProblem P = h->P;
+    P.node_begin = (long long)p0 * h->plane;
+    P.node_end = (long long)p1 * h->plane;
+    P.plane_begin = (long long)p0 * P.dims[1];
+    const long long nodes = P.node_end - P.node_begin;
+    const double* Jn = h->Jv(h->cur_idx);
+    double* Jo = h->Jv(1 - h->cur_idx);
+    unsigned long long* slots = h->dslots + (size_t)stat_set * 3 * STATS_SLOTS;
+    unsigned int* counter = h->dcounter + stat_set;
+    if (nodes <= 0) {
         const double ident[3] = {-__builtin_inf(), -__builtin_inf(), __builtin_inf()};
-        CUDA_TRY(h, cudaMemcpyAsync(stats, ident, sizeof(ident), cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(h, cudaMemcpyAsync(stats, ident, sizeof(ident), cudaMemcpyHostToDevice, stream));
         return PDP_OK;
     }
     if (P.system_id == PDP_SYS_LUT) {
         if (!h->have_lut) return fail(h, PDP_ESTATE, "pdp_sweep: LUT mode needs pdp_set_lut first");
         int G = 1;
         while (G < 32 && G < P.A) G <<= 1;
-        const long long threads = slab_nodes * G;
-        const unsigned blocks = (unsigned)((threads + SWEEP_THREADS - 1) / SWEEP_THREADS);
-        if (P.n == 2) launch_lut<2>(h, G, blocks, Jn, Jo, stats);
-        else if (P.n == 3) launch_lut<3>(h, G, blocks, Jn, Jo, stats);
-        else launch_lut<4>(h, G, blocks, Jn, Jo, stats);
+        const long long blocks = (nodes * G + SWEEP_THREADS - 1) / SWEEP_THREADS;
+        if (blocks > 0x7fffffffLL) return fail(h, PDP_ENOTSUP, "grid too large for one launch");
+        if (P.n == 2) launch_lut<2>(h, stream, P, G, (unsigned)blocks, Jn, Jo, slots, counter, stats);
+        else if (P.n == 3) launch_lut<3>(h, stream, P, G, (unsigned)blocks, Jn, Jo, slots, counter, stats);
+        else launch_lut<4>(h, stream, P, G, (unsigned)blocks, Jn, Jo, slots, counter, stats);
     } else {
-        ((fused_kernel_t)h->fused)<<<h->grid, SWEEP_THREADS, h->smem_bytes, h->stream>>>(P, Jn, Jo, h->dpi, h->dpartials, h->dcounter, stats);
+        const int G = h->lanes_per_node;
+        dim3 grid;
+        if (P.system_id == PDP_SYS_PENDULUM) {
+            grid = dim3((unsigned)((nodes * G + SWEEP_THREADS - 1) / SWEEP_THREADS), 1, 1);
+        } else {
+            const long long plane_sz = (long long)P.dims[2] * P.dims[3];
+            const long long pairs = (long long)(p1 - p0) * P.dims[1];
+            if (pairs > 0x7fffffffLL) return fail(h, PDP_ENOTSUP, "grid too large for one launch");
+            grid = dim3((unsigned)pairs, (unsigned)((plane_sz * G + SWEEP_THREADS - 1) / SWEEP_THREADS), 1);
+        }
+        ((fused_kernel_t)h->fused)<<<grid, SWEEP_THREADS, h->smem_bytes, stream>>>(P, Jn, Jo, h->piv(), slots, counter, stats);
     }
     CUDA_TRY(h, cudaGetLastError());
     h->launches += 1;
@@ -585,7 +726,19 @@ extern "C" int pdp_sweep_async(pdp_handle* h) {
     CHECK_HANDLE(h);
     if (!h->have_J) return fail(h, PDP_ESTATE, "pdp_sweep: no cost-to-go yet (pdp_set_J / pdp_eval_terminal_cost)");
     if (h->pending) return fail(h, PDP_ESTATE, "pdp_sweep_async: previous sweep not committed");
-    int rc = launch_sweep(h, h->dstats);
+    int rc = launch_planes(h, h->slab_begin, h->slab_end, 0, h->dstats_sets);
+    if (rc != PDP_OK) return rc;
+    h->pending = true;
+    return PDP_OK;
+}
+
+extern "C" int pdp_sweep_planes_async(pdp_handle* h, int32_t plane_begin, int32_t plane_end, int32_t stat_set) {
+    CHECK_HANDLE(h);
+    if (!h->have_J) return fail(h, PDP_ESTATE, "pdp_sweep: no cost-to-go yet (pdp_set_J / pdp_eval_terminal_cost)");
+    if (plane_begin < h->slab_begin || plane_end > h->slab_end || plane_begin > plane_end)
+        return fail(h, PDP_EINVAL, "pdp_sweep_planes_async: plane range outside this handle's slab");
+    if (stat_set < 0 || stat_set >= PDP_STAT_SETS) return fail(h, PDP_EINVAL, "pdp_sweep_planes_async: stat_set out of range");
+    int rc = launch_planes(h, plane_begin, plane_end, stat_set, h->dstats_sets + 3 * stat_set);
     if (rc != PDP_OK) return rc;
     h->pending = true;
     return PDP_OK;
@@ -599,57 +752,231 @@ extern "C" int pdp_commit_sweep(pdp_handle* h) {
     return PDP_OK;
 }
 
+extern "C" int pdp_read_stats(pdp_handle* h, double* stats_host) {
+    CHECK_HANDLE(h);
+    if (!stats_host) return fail(h, PDP_EINVAL, "pdp_read_stats: null pointer");
+    return copy_out(h, stats_host, h->dstats_sets, (size_t)PDP_STAT_SETS * 3 * sizeof(double));
+}
+
 extern "C" int pdp_device_buffers(pdp_handle* h, void** J_cur, void** J_new, void** pi, void** stats) {
     CHECK_HANDLE(h);
     if (J_cur) *J_cur = h->dJ[h->cur_idx];
     if (J_new) *J_new = h->dJ[1 - h->cur_idx];
     if (pi) *pi = h->dpi;
-    if (stats) *stats = h->dstats;
+    if (stats) *stats = h->dstats_sets;
+    return PDP_OK;
+}
+
+// ---- multi-GPU: NCCL through dlopen (the process-wide libnccl.so.2, i.e. the one torch already loaded) ----
+static int nccl_load() {
+    if (g_nccl.lib) return PDP_OK;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return fail(nullptr, PDP_ECUDA, std::string("cannot load libnccl.so.2: ") + dlerror());
+#define NCCL_SYM(field, name)                                                              \
+    *(void**)(&g_nccl.field) = dlsym(lib, name);                                           \
+    if (!g_nccl.field) return fail(nullptr, PDP_ECUDA, std::string("libnccl.so.2 lacks ") + name);
+    NCCL_SYM(GetUniqueId, "ncclGetUniqueId") NCCL_SYM(CommInitRank, "ncclCommInitRank")
+    NCCL_SYM(CommDestroy, "ncclCommDestroy") NCCL_SYM(Send, "ncclSend") NCCL_SYM(Recv, "ncclRecv")
+    NCCL_SYM(GroupStart, "ncclGroupStart") NCCL_SYM(GroupEnd, "ncclGroupEnd")
+    NCCL_SYM(AllReduce, "ncclAllReduce") NCCL_SYM(AllGather, "ncclAllGather")
+    NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef NCCL_SYM
+    g_nccl.lib = lib;
+    return PDP_OK;
+}
+
+#define NCCL_TRY(h, expr)                                                                            \
+    do {                                                                                             \
+        int _r = (expr);                                                                             \
+        if (_r != 0) return fail(h, PDP_ECUDA, std::string(#expr) + ": " + g_nccl.GetErrorString(_r)); \
+    } while (0)
+
+extern "C" int pdp_nccl_unique_id(void* id128) {
+    if (!id128) return fail(nullptr, PDP_EINVAL, "pdp_nccl_unique_id: null pointer");
+    int rc = nccl_load();
+    if (rc != PDP_OK) return rc;
+    NCCL_TRY(nullptr, g_nccl.GetUniqueId((pdp_nccl_id*)id128));
+    return PDP_OK;
+}
+
+extern "C" int pdp_comm_init(pdp_handle* h, int32_t rank, int32_t world, const void* id128, int32_t exchange_mode,
+                             int32_t overlap) {
+    CHECK_HANDLE(h);
+    if (!id128 || world < 1 || rank < 0 || rank >= world) return fail(h, PDP_EINVAL, "pdp_comm_init: bad rank / world / id");
+    if (exchange_mode != 1 && exchange_mode != 2) return fail(h, PDP_EINVAL, "pdp_comm_init: exchange_mode must be 1 (halo) or 2 (all-gather)");
+    if (h->comm) return fail(h, PDP_ESTATE, "pdp_comm_init: communicator already attached");
+    if (exchange_mode == 2 && (h->alloc_begin != 0 || h->alloc_end != h->n0 || h->alloc_planes_cap % world != 0 ||
+                               (long long)h->slab_begin != std::min<long long>((long long)rank * (h->alloc_planes_cap / world), h->n0)))
+        return fail(h, PDP_EINVAL, "pdp_comm_init: all-gather mode needs the whole grid in buffers of W*ceil(dims[0]/W) planes "
+                                   "and slab r = planes [r*P, (r+1)*P)");
+    if (exchange_mode == 1 && world > 1) {
+        const bool lo_ok = rank == 0 || (h->alloc_begin == h->slab_begin - h->halo_lo);
+        const bool hi_ok = rank == world - 1 || (h->alloc_end == h->slab_end + h->halo_hi);
+        if (!lo_ok || !hi_ok || h->slab_end - h->slab_begin < std::max(h->halo_lo, h->halo_hi))
+            return fail(h, PDP_EINVAL, "pdp_comm_init: halo mode needs slab + halo buffers and a slab at least as thick as the halo");
+    }
+    int rc = nccl_load();
+    if (rc != PDP_OK) return fail(h, rc, g_err);
+    pdp_nccl_id id;
+    memcpy(&id, id128, sizeof(id));
+    NCCL_TRY(h, g_nccl.CommInitRank(&h->comm, world, id, rank));
+    h->rank = rank; h->world = world; h->exchange_mode = exchange_mode; h->overlap = overlap;
+    int prio_lo = 0, prio_hi = 0;
+    CUDA_TRY(h, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CUDA_TRY(h, cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, prio_hi));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_boundary, cudaEventDisableTiming));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming));
+    return PDP_OK;
+}
+
+// Complete buffer `which` on this rank after its slab planes were (re)written: halo planes from the
+// neighbouring ranks (grouped send/recv), or the in-place all-gather of whole slabs.
+static int exchange(pdp_handle* h, int which, cudaStream_t st) {
+    if (!h->comm || h->world == 1) return PDP_OK;
+    double* base = h->dJ[which];  // element 0 = plane alloc_begin
+    auto at = [&](int plane) { return base + (long long)(plane - h->alloc_begin) * h->plane; };
+    h->exchanges += 1;
+    if (h->exchange_mode == 2) {
+        const size_t cnt = (size_t)(h->alloc_planes_cap / h->world) * h->plane;
+        NCCL_TRY(h, g_nccl.AllGather(base + (size_t)h->rank * cnt, base, cnt, PDP_NCCL_F64, h->comm, st));
+        return PDP_OK;
+    }
+    const size_t nlo = (size_t)h->halo_lo * h->plane, nhi = (size_t)h->halo_hi * h->plane;
+    NCCL_TRY(h, g_nccl.GroupStart());
+    if (h->rank > 0) {  // rank r-1 reads my lowest halo_hi planes; I read its highest halo_lo planes
+        NCCL_TRY(h, g_nccl.Send(at(h->slab_begin), nhi, PDP_NCCL_F64, h->rank - 1, h->comm, st));
+        NCCL_TRY(h, g_nccl.Recv(at(h->slab_begin - h->halo_lo), nlo, PDP_NCCL_F64, h->rank - 1, h->comm, st));
+    }
+    if (h->rank < h->world - 1) {
+        NCCL_TRY(h, g_nccl.Send(at(h->slab_end - h->halo_lo), nlo, PDP_NCCL_F64, h->rank + 1, h->comm, st));
+        NCCL_TRY(h, g_nccl.Recv(at(h->slab_end), nhi, PDP_NCCL_F64, h->rank + 1, h->comm, st));
+    }
+    NCCL_TRY(h, g_nccl.GroupEnd());
+    return PDP_OK;
+}
+
+// One sweep of this rank's slab + exchange, enqueued without host synchronisation; the folded
+// statistics {jmax, dmax, -dmin} of the slab go to dst[0..2].
+static int sharded_sweep_enqueue(pdp_handle* h, double* dst) {
+    const int b = h->slab_begin, e = h->slab_end, lo = h->halo_lo, hi = h->halo_hi;
+    double* sets = h->dstats_sets;
+    int rc;
+    if (h->exchange_mode == 1 && h->overlap && b + hi < e - lo) {
+        // Boundary planes + their exchange on the high-priority side stream, interior planes on the
+        // main stream: the two kernels share the SMs (no serialised tail), the boundary blocks are
+        // scheduled first, and the NCCL send/recv runs under the interior planes.
+        CUDA_TRY(h, cudaEventRecord(h->ev_boundary, h->stream));            // previous sweep (and its exchange) done
+        CUDA_TRY(h, cudaStreamWaitEvent(h->comm_stream, h->ev_boundary, 0));
+        if ((rc = launch_planes(h, b, b + hi, 1, sets + 3, h->comm_stream)) != PDP_OK) return rc;
+        if ((rc = launch_planes(h, e - lo, e, 2, sets + 6, h->comm_stream)) != PDP_OK) return rc;
+        if ((rc = exchange(h, 1 - h->cur_idx, h->comm_stream)) != PDP_OK) return rc;
+        CUDA_TRY(h, cudaEventRecord(h->ev_comm, h->comm_stream));
+        if ((rc = launch_planes(h, b + hi, e - lo, 0, sets)) != PDP_OK) return rc;
+        CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
+        stats_fold_kernel<<<1, 1, 0, h->stream>>>(sets, 3, dst);
+    } else {
+        if ((rc = launch_planes(h, b, e, 0, sets)) != PDP_OK) return rc;
+        if ((rc = exchange(h, 1 - h->cur_idx, h->stream)) != PDP_OK) return rc;
+        stats_fold_kernel<<<1, 1, 0, h->stream>>>(sets, 1, dst);
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    h->cur_idx = 1 - h->cur_idx;
+    return PDP_OK;
+}
+
+// Enqueue one full sweep (all of this handle's planes, plus the exchange when a communicator is
+// attached) without host synchronisation; its statistics go to the next slot of the history.
+extern "C" int pdp_sweep_enqueue(pdp_handle* h) {
+    CHECK_HANDLE(h);
+    if (!h->have_J) return fail(h, PDP_ESTATE, "pdp_sweep: no cost-to-go yet (pdp_set_J / pdp_eval_terminal_cost)");
+    if (h->pending) return fail(h, PDP_ESTATE, "pdp_sweep: an async sweep is pending");
+    const bool sharded = h->comm && h->world > 1;
+    if (!sharded && h->slab_nodes() != h->N)
+        return fail(h, PDP_ESTATE, "pdp_sweep: handle owns a slab only; attach a communicator (pdp_comm_init) or drive it with "
+                                   "pdp_sweep_async + exchange + pdp_commit_sweep");
+    if (h->enqueued >= h->stats_cap) {  // grow the history, keeping what is there
+        double* bigger = nullptr;
+        const int cap = h->stats_cap * 2;
+        CUDA_TRY(h, cudaMalloc(&bigger, (size_t)cap * 3 * sizeof(double)));
+        CUDA_TRY(h, cudaMemcpyAsync(bigger, h->dstats, (size_t)h->stats_cap * 3 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        CUDA_TRY(h, cudaFree(h->dstats));
+        h->dstats = bigger;
+        h->stats_cap = cap;
+    }
+    double* dst = h->dstats + 3 * h->enqueued;
+    int rc;
+    if (sharded) {
+        rc = sharded_sweep_enqueue(h, dst);
+    } else {
+        rc = launch_planes(h, h->slab_begin, h->slab_end, 0, dst);
+        if (rc == PDP_OK) h->cur_idx = 1 - h->cur_idx;
+    }
+    if (rc != PDP_OK) return rc;
+    h->enqueued += 1;
+    return PDP_OK;
+}
+
+// Wait for the enqueued sweeps, reduce their statistics over the ranks (one all-reduce of 3 doubles
+// per sweep) and copy up to max_out of them (oldest first) to the host.
+extern "C" int pdp_sweep_collect(pdp_handle* h, pdp_stats* stats_out, int32_t max_out, int32_t* n_out) {
+    CHECK_HANDLE(h);
+    const int n = h->enqueued;
+    if (n_out) *n_out = std::min(n, (int)max_out);
+    if (n > 0 && h->comm && h->world > 1) {
+        NCCL_TRY(h, g_nccl.AllReduce(h->dstats, h->dstats, (size_t)3 * n, PDP_NCCL_F64, PDP_NCCL_MAX, h->comm, h->stream));
+        stats_unfold_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(h->dstats, n);
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    const int m = std::min(n, (int)max_out);
+    if (stats_out && m > 0)
+        CUDA_TRY(h, cudaMemcpyAsync(stats_out, h->dstats, (size_t)m * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->enqueued = 0;
     return PDP_OK;
 }
 
 extern "C" int pdp_sweep(pdp_handle* h, int32_t n_sweeps, pdp_stats* stats_out) {
     CHECK_HANDLE(h);
     if (n_sweeps < 0) return fail(h, PDP_EINVAL, "pdp_sweep: n_sweeps < 0");
-    if (!h->have_J) return fail(h, PDP_ESTATE, "pdp_sweep: no cost-to-go yet (pdp_set_J / pdp_eval_terminal_cost)");
-    if (h->pending) return fail(h, PDP_ESTATE, "pdp_sweep: an async sweep is pending");
-    if (h->P.node_end - h->P.node_begin != h->N)
-        return fail(h, PDP_ESTATE, "pdp_sweep: handle owns a slab only; drive it with pdp_sweep_async + exchange + pdp_commit_sweep");
-    if (n_sweeps > h->stats_cap) {
-        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-        CUDA_TRY(h, cudaFree(h->dstats));
-        h->dstats = nullptr;
-        h->stats_cap = n_sweeps;
-        CUDA_TRY(h, cudaMalloc(&h->dstats, (size_t)h->stats_cap * 3 * sizeof(double)));
-    }
+    if (h->enqueued) return fail(h, PDP_ESTATE, "pdp_sweep: collect the enqueued sweeps first (pdp_sweep_collect)");
     CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
     for (int k = 0; k < n_sweeps; ++k) {
-        int rc = launch_sweep(h, h->dstats + 3 * k);
-        if (rc != PDP_OK) return rc;
-        h->cur_idx = 1 - h->cur_idx;
+        int rc = pdp_sweep_enqueue(h);
+        if (rc != PDP_OK) { h->enqueued = 0; return rc; }
     }
     CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
-    if (stats_out && n_sweeps > 0)
-        CUDA_TRY(h, cudaMemcpyAsync(stats_out, h->dstats, (size_t)n_sweeps * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    int rc = pdp_sweep_collect(h, stats_out, n_sweeps, nullptr);
+    if (rc != PDP_OK) return rc;
     float ms = 0.f;
     CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->last_ms = ms;
     return PDP_OK;
 }
 
+// exchange the halo planes of the CURRENT J (after pdp_set_J with rank-local data or pdp_clean_infeasible_set)
+extern "C" int pdp_exchange_current(pdp_handle* h) {
+    CHECK_HANDLE(h);
+    int rc = exchange(h, h->cur_idx, h->stream);
+    if (rc != PDP_OK) return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return PDP_OK;
+}
+
+// u_k of this handle's slab (slab_nodes doubles)
 extern "C" int pdp_get_input_from_policy(pdp_handle* h, int32_t k, double* uk_host) {
     CHECK_HANDLE(h);
     if (k < 0 || k >= h->P.m) return fail(h, PDP_EINVAL, "pdp_get_input_from_policy: input axis out of range");
     if (!uk_host) return fail(h, PDP_EINVAL, "pdp_get_input_from_policy: null pointer");
-    double* scratch = h->dJ[1 - h->cur_idx];  // J_next is scratch only until the next sweep overwrites it anyway
+    const long long n = h->slab_nodes();
+    if (n == 0) return PDP_OK;
     double* tmp = nullptr;
-    CUDA_TRY(h, cudaMalloc(&tmp, h->N * sizeof(double)));
-    (void)scratch;
+    CUDA_TRY(h, cudaMalloc(&tmp, n * sizeof(double)));
     const int threads = 256;
-    input_from_policy_kernel<<<(unsigned)((h->N + threads - 1) / threads), threads, 0, h->stream>>>(h->dpi, h->P.u_flat, h->P.m, k, tmp, h->N);
+    input_from_policy_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, h->stream>>>(h->dpi, h->P.u_flat, h->P.m, k, tmp, n);
     cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(uk_host, tmp, h->N * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(uk_host, tmp, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     cudaFree(tmp);
     if (e != cudaSuccess) return fail(h, PDP_ECUDA, std::string("pdp_get_input_from_policy: ") + cudaGetErrorString(e));
@@ -659,9 +986,11 @@ extern "C" int pdp_get_input_from_policy(pdp_handle* h, int32_t k, double* uk_ho
 extern "C" int pdp_clean_infeasible_set(pdp_handle* h, double tol, int64_t default_action) {
     CHECK_HANDLE(h);
     if (default_action < 0 || default_action >= h->A) return fail(h, PDP_EINVAL, "pdp_clean_infeasible_set: default action out of range");
+    const long long n = h->slab_nodes();
+    if (n == 0) return PDP_OK;
     const int threads = 256;
-    clean_infeasible_kernel<<<(unsigned)((h->N + threads - 1) / threads), threads, 0, h->stream>>>(
-        h->dJ[h->cur_idx], h->dpi, h->P.INF - tol, h->P.INF, (long long)default_action, h->N);
+    clean_infeasible_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, h->stream>>>(
+        h->Jv(h->cur_idx) + h->P.slab_node_begin, h->dpi, h->P.INF - tol, h->P.INF, (long long)default_action, n);
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return PDP_OK;

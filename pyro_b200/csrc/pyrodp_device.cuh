@@ -27,7 +27,8 @@ struct DevProblem {
     const unsigned char* act_ok;  // [A]
     const double* u_flat;      // [A*m] input_from_action_id
     long long node_begin, node_end, N;
-    long long plane_begin;          // first (i0,i1) pair of the slab = slab_begin * dims[1] (4-D kernels)
+    long long plane_begin;          // first (i0,i1) pair of this launch = first plane * dims[1] (4-D kernels)
+    long long slab_node_begin;      // first node of the handle's slab (origin of slab-local tables, LUT mode)
 };
 
 // ---- np.dot conventions of the reference's BLAS (OpenBLAS 0.3.30 SkylakeX kernels) -----------

@@ -17,6 +17,12 @@ class Engine:
         h = C.c_void_p()
         _lib.check(self.lib.pdp_create(C.byref(problem.c), C.byref(h)))
         self.h = h
+        lay = (C.c_int32 * 8)()
+        self._ck(self.lib.pdp_slab_layout(self.h, lay))
+        (self.slab_begin, self.slab_end, self.alloc_begin, self.alloc_end,
+         self.halo_lo, self.halo_hi, self.n0, self.lanes_per_node) = (int(v) for v in lay)
+        self.plane = self.N // self.n0
+        self.slab_nodes = (self.slab_end - self.slab_begin) * self.plane
 
     def close(self):
         if getattr(self, "h", None):
@@ -42,27 +48,33 @@ class Engine:
             raise ValueError("Grid size does not match data")
         self._ck(self.lib.pdp_set_J(self.h, J.ctypes.data))
 
+    # getters return this handle's slab (the whole grid on a single GPU)
+    def _out(self, out, dtype):
+        if out is None:
+            return np.empty(self.slab_nodes, dtype=dtype)
+        if out.size != self.slab_nodes or out.dtype != dtype or not out.flags.c_contiguous:
+            raise ValueError("output buffer does not match the slab size / dtype")
+        return out
+
     def get_J(self, out=None):
-        out = np.empty(self.N, dtype=np.float64) if out is None else out
+        out = self._out(out, np.float64)
         self._ck(self.lib.pdp_get_J(self.h, out.ctypes.data))
         return out
 
     def get_J_next(self, out=None):
-        out = np.empty(self.N, dtype=np.float64) if out is None else out
+        out = self._out(out, np.float64)
         self._ck(self.lib.pdp_get_J_next(self.h, out.ctypes.data))
         return out
 
     def get_pi(self, out=None):
-        out = np.empty(self.N, dtype=np.int64) if out is None else out
+        out = self._out(out, np.int64)
         self._ck(self.lib.pdp_get_pi(self.h, out.ctypes.data))
         return out
 
     def set_lut(self, x_next, G):
         x_next = np.ascontiguousarray(x_next, dtype=np.float64)
         G = np.ascontiguousarray(G, dtype=np.float64)
-        c = self.problem.c
-        slab_nodes = (c.slab_end - c.slab_begin) * (self.N // c.dims[0])
-        if x_next.size != slab_nodes * self.A * self.n or G.size != slab_nodes * self.A:
+        if x_next.size != self.slab_nodes * self.A * self.n or G.size != self.slab_nodes * self.A:
             raise ValueError("look-up table size does not match the grid")
         self._ck(self.lib.pdp_set_lut(self.h, x_next.ctypes.data, G.ctypes.data))
 
@@ -73,8 +85,39 @@ class Engine:
         self._ck(self.lib.pdp_sweep(self.h, int(n_sweeps), stats.ctypes.data))
         return stats
 
+    def sweep_nowait(self):
+        """Enqueue one sweep (+ exchange when a communicator is attached) without blocking."""
+        self._ck(self.lib.pdp_sweep_enqueue(self.h))
+        self._enqueued = getattr(self, "_enqueued", 0) + 1
+
+    def collect_stats(self):
+        """Wait for the enqueued sweeps; (k, 3) array of [j_max, delta_max, delta_min], reduced over ranks."""
+        n = getattr(self, "_enqueued", 0)
+        out = np.empty((max(n, 1), 3), dtype=np.float64)
+        got = C.c_int32(0)
+        self._ck(self.lib.pdp_sweep_collect(self.h, out.ctypes.data, n, C.byref(got)))
+        self._enqueued = 0
+        return out[:got.value]
+
+    # ---- multi-GPU: native NCCL exchange inside the library ----
+    def nccl_unique_id(self):
+        buf = C.create_string_buffer(128)
+        self._ck(self.lib.pdp_nccl_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, rank, world, unique_id, mode, overlap=True):
+        """mode: 'halo' (send/recv with ranks r-1 / r+1) or 'allgather' (whole slabs)."""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._ck(self.lib.pdp_comm_init(self.h, int(rank), int(world), buf, {"halo": 1, "allgather": 2}[mode], int(bool(overlap))))
+
+    def exchange_current(self):
+        self._ck(self.lib.pdp_exchange_current(self.h))
+
     def sweep_async(self):
         self._ck(self.lib.pdp_sweep_async(self.h))
+
+    def sweep_planes_async(self, plane_begin, plane_end, stat_set=0):
+        self._ck(self.lib.pdp_sweep_planes_async(self.h, int(plane_begin), int(plane_end), int(stat_set)))
 
     def commit_sweep(self):
         self._ck(self.lib.pdp_commit_sweep(self.h))
@@ -89,7 +132,7 @@ class Engine:
 
     # ---- after the sweep ----
     def get_input_from_policy(self, k):
-        out = np.empty(self.N, dtype=np.float64)
+        out = np.empty(self.slab_nodes, dtype=np.float64)
         self._ck(self.lib.pdp_get_input_from_policy(self.h, int(k), out.ctypes.data))
         return out
 

@@ -1,0 +1,86 @@
+"""Multi-GPU parity check, run under torchrun (one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multigpu_check.py
+
+Every rank drives its slab through ``pyro_b200.distributed.ShardedEngine`` (NCCL) and the gathered
+J / pi must equal the reference goldens bit for bit, in every exchange mode: halo send/recv with
+boundary-first overlap, halo send/recv without overlap, and the all-gather fallback.
+tests/test_multigpu.py launches this when the box has >= 2 GPUs.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from pyro_b200 import distributed, problem
+    from pyro_b200.engine import Engine
+    from tests.cases import CASES, build_case
+    from tests.conftest import load_golden
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    failures = 0
+    for name in ("pend_51x51x11", "pend_101x101x21", "pend_time_41x61x7", "dpend_example", "twolink_soft", "cartpole_swingup"):
+        case, gold = CASES[name], load_golden(name)
+        _, grid, cf = build_case(case)
+        k = case["snapshots"][1]
+        for mode, overlap, backend in (("halo", True, "native"), ("halo", False, "native"), ("allgather", False, "native"),
+                                       ("halo", True, "torch"), ("allgather", False, "torch")):
+            try:
+                eng = distributed.ShardedEngine(grid, cf, case.get("alpha", 1.0), mode=mode, overlap=overlap, backend=backend)
+            except ValueError:
+                if rank == 0:
+                    print(f"[multigpu] {name} {mode}: halo does not fit {world} ranks, skipped")
+                continue
+            eng.eval_terminal_cost()
+            stats = eng.sweep(k)
+            J, pi, Jn = eng.get_J(), eng.get_pi(), eng.get_J_next()
+            ok = np.array_equal(J, gold[f"J_{k}"]) and np.array_equal(pi, gold[f"pi_{k}"])
+            d = J - Jn
+            ok = ok and stats[-1, 0] == J.max() and stats[-1, 1] == d.max() and stats[-1, 2] == d.min()
+            held = eng.alloc_end - eng.alloc_begin
+            if rank == 0:
+                print(f"[multigpu] {name} W={world} {eng.backend} mode={eng.mode} overlap={eng.overlap} k={k} planes held {held}/{eng.n0} "
+                      f"halo=({eng.halo_lo},{eng.halo_hi}): {'OK' if ok else 'MISMATCH'}", flush=True)
+            failures += 0 if ok else 1
+            eng.close()
+    # mid-size random-J check against a single-GPU engine on the same device (rough J, every corner weight matters)
+    case = dict(system="CartPole", x_grid_dim=[33, 21, 19, 23], u_grid_dim=[9], xbar=[0.0, float(np.pi), 0.0, 0.0], INF=1000.0)
+    _, grid, cf = build_case(case)
+    J0 = np.random.default_rng(7).uniform(0, 300, grid.nodes_n)
+    single = Engine(problem.extract(grid, cf, 1.0))
+    single.set_J(J0)
+    single.sweep(3)
+    Jref, piref = single.get_J(), single.get_pi()
+    single.close()
+    for overlap in (True, False):
+        eng = distributed.ShardedEngine(grid, cf, 1.0, overlap=overlap)
+        eng.set_J(J0)
+        eng.sweep_nowait()            # the non-blocking form the benchmark uses
+        eng.sweep_nowait()
+        assert eng.collect_stats().shape == (2, 3)
+        eng.sweep(1)
+        ok = np.array_equal(eng.get_J(), Jref) and np.array_equal(eng.get_pi(), piref)
+        if rank == 0:
+            print(f"[multigpu] cartpole 33x21x19x23 random J W={world} mode={eng.mode} overlap={eng.overlap}: {'OK' if ok else 'MISMATCH'}", flush=True)
+        failures += 0 if ok else 1
+        eng.close()
+    t = torch.tensor([failures], device="cuda")
+    dist.all_reduce(t)
+    if rank == 0:
+        print(f"[multigpu] {'ALL OK' if t.item() == 0 else 'FAILURES: %d' % t.item()}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if t.item() == 0 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -18,7 +18,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, name, n_sweeps, q):
+def _worker(rank, world, port, name, n_sweeps, mode, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -26,23 +26,31 @@ def _worker(rank, world, port, name, n_sweeps, q):
         from tests.fake_engine import FakeEngine
         case = CASES[name]
         _, grid, cf = build_case(case)
-        eng = distributed.ShardedEngine(grid, cf, case.get("alpha", 1.0), engine_factory=FakeEngine)
+        eng = distributed.ShardedEngine(grid, cf, case.get("alpha", 1.0), engine_factory=FakeEngine, mode=mode)
         eng.eval_terminal_cost()
         stats = eng.sweep(n_sweeps)
-        J, pi = eng.get_J(), eng.get_pi()
-        q.put((rank, J, pi, stats, (eng.begin, eng.end)))
+        J, pi, Jn = eng.get_J(), eng.get_pi(), eng.get_J_next()
+        held = (eng.alloc_end - eng.alloc_begin, eng.halo_lo, eng.halo_hi)
+        q.put((rank, J, pi, stats, (eng.begin, eng.end), eng.mode, held, Jn))
         dist.barrier()
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name,world,k", [("pend_51x51x11", 2, 10), ("dpend_example", 2, 2), ("cartpole_swingup", 3, 2)])
-def test_sharded_sweeps_equal_single_rank_goldens(name, world, k):
+@pytest.mark.parametrize("name,world,k,mode,expect", [
+    ("pend_51x51x11", 2, 10, None, "halo"),          # neighbour send/recv of halo planes
+    ("dpend_example", 2, 2, None, "halo"),
+    ("cartpole_swingup", 3, 2, None, "halo"),        # middle rank exchanges on both sides
+    ("pend_51x51x11", 3, 2, "allgather", "allgather"),  # forced fallback: in-place all-gather of whole slabs
+    ("twolink_9", 8, 1, None, "halo"),               # 9 planes on 8 ranks, one-plane halos: still neighbour exchange
+    ("dpend_example", 6, 1, None, "allgather"),      # halo (2 planes) wider than a slab (1): automatic fallback
+])
+def test_sharded_sweeps_equal_single_rank_goldens(name, world, k, mode, expect):
     gold = load_golden(name)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, name, k, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, name, k, mode, q)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=300) for _ in range(world)]
@@ -51,7 +59,13 @@ def test_sharded_sweeps_equal_single_rank_goldens(name, world, k):
         assert p.exitcode == 0
     slabs = sorted(r[4] for r in results)
     assert slabs[0][0] == 0 and slabs[-1][1] == CASES[name]["x_grid_dim"][0]
-    for rank, J, pi, stats, _ in results:
+    n0 = CASES[name]["x_grid_dim"][0]
+    for rank, J, pi, stats, slab, got_mode, held, Jn in results:
+        assert got_mode == expect
+        if expect == "halo":   # memory per rank is slab + halo, not the whole grid
+            assert held[0] <= (slab[1] - slab[0]) + held[1] + held[2] and (world == 1 or held[0] < n0)
+        if f"J_{k-1}" in gold.files:
+            assert np.array_equal(Jn, gold[f"J_{k-1}"])
         assert np.array_equal(J, gold[f"J_{k}"]), f"rank {rank}: J differs"
         assert np.array_equal(pi, gold[f"pi_{k}"]), f"rank {rank}: pi differs"
         d = gold[f"J_{k}"] - (gold[f"J_{k-1}"] if f"J_{k-1}" in gold.files else J * np.nan)
