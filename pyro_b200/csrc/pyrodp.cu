@@ -297,9 +297,9 @@ static int expected_tab_len(const pdp_problem* p, int t, long long* len) {
 typedef void (*fused_kernel_t)(const DevProblem, const double*, double*, long long*, unsigned long long*, unsigned int*, double*);
 
 template <int G, bool A1>
-static fused_kernel_t fused_for(int system_id) {
+static fused_kernel_t fused_for(int system_id, bool nodamp) {
     switch (system_id) {
-        case PDP_SYS_PENDULUM: return sweep_pendulum_kernel<G, A1>;
+        case PDP_SYS_PENDULUM: return nodamp ? sweep_pendulum_kernel<G, A1, true> : sweep_pendulum_kernel<G, A1, false>;
         case PDP_SYS_TWOLINK: return sweep_mech2_kernel<PDP_SYS_TWOLINK, G, A1>;
         case PDP_SYS_CARTPOLE: return sweep_mech2_kernel<PDP_SYS_CARTPOLE, G, A1>;
     }
@@ -320,9 +320,10 @@ static int select_fused_kernel(pdp_handle* h) {
     if (h->force_lanes == 1 || h->force_lanes == 4 || h->force_lanes == 16) G = h->force_lanes;
     const bool a1 = P.alpha_is_one != 0;
     fused_kernel_t k = nullptr;
-    if (G == 1) k = a1 ? fused_for<1, true>(P.system_id) : fused_for<1, false>(P.system_id);
-    else if (G == 4) k = a1 ? fused_for<4, true>(P.system_id) : fused_for<4, false>(P.system_id);
-    else k = a1 ? fused_for<16, true>(P.system_id) : fused_for<16, false>(P.system_id);
+    const bool nd = (P.system_id == PDP_SYS_PENDULUM) && P.par[1] == 0.0;  // d1 == 0: no damping term
+    if (G == 1) k = a1 ? fused_for<1, true>(P.system_id, nd) : fused_for<1, false>(P.system_id, nd);
+    else if (G == 4) k = a1 ? fused_for<4, true>(P.system_id, nd) : fused_for<4, false>(P.system_id, nd);
+    else k = a1 ? fused_for<16, true>(P.system_id, nd) : fused_for<16, false>(P.system_id, nd);
     if (!k) return fail(h, PDP_ENOTSUP, "no fused kernel for this system");
     h->lanes_per_node = G;
     h->fused = (void*)k;
@@ -331,6 +332,8 @@ static int select_fused_kernel(pdp_handle* h) {
         const size_t n1p = (size_t)((P.dims[1] + 1) & ~1);
         h->smem_bytes = (2 * n1p + 2 * A) * sizeof(double) + 16;
         if (h->N > 0x7fffffffLL) return fail(h, PDP_ENOTSUP, "2-D grids are limited to 2^31-1 nodes");
+        if (((long long)P.dims[1] * G + SWEEP_THREADS - 1) / SWEEP_THREADS > 65535)
+            return fail(h, PDP_ENOTSUP, "grid too large for one launch (dims[1] too big)");
     } else {
         const size_t n2p = (size_t)((P.dims[2] + 1) & ~1), n3p = (size_t)((P.dims[3] + 1) & ~1);
         h->smem_bytes = (2 * n2p + 2 * n3p + 4 * A) * sizeof(double) + 16;
@@ -708,7 +711,8 @@ static int launch_planes(pdp_handle* h, int p0, int p1, int stat_set, double* st
         const int G = h->lanes_per_node;
         dim3 grid;
         if (P.system_id == PDP_SYS_PENDULUM) {
-            grid = dim3((unsigned)((nodes * G + SWEEP_THREADS - 1) / SWEEP_THREADS), 1, 1);
+            P.plane_begin = p0;  // blockIdx.x = row of the plane range, blockIdx.y = chunk of the row
+            grid = dim3((unsigned)(p1 - p0), (unsigned)(((long long)P.dims[1] * G + SWEEP_THREADS - 1) / SWEEP_THREADS), 1);
         } else {
             const long long plane_sz = (long long)P.dims[2] * P.dims[3];
             const long long pairs = (long long)(p1 - p0) * P.dims[1];
