@@ -357,11 +357,21 @@ def main():
         held = (kernel_eng.alloc_end - kernel_eng.alloc_begin) * kernel_eng.plane
         n_e2e = max(3, min(args.steps, 10))
 
-        def e2e_step():
-            eng.set_J(J_np)             # H2D: J_next planes this rank holds
-            eng.sweep(1)                # sweep (+ halo exchange and stats all-reduce for N>1)
-            kernel_eng.get_J(Js_np)     # D2H: J of the slab
-            kernel_eng.get_pi(pis_np)   # D2H: pi of the slab
+        if world == 1:
+            J_in = torch.empty(N, dtype=torch.float64).pin_memory()
+            J_in.copy_(torch.from_numpy(Js_np))   # the current J: every timed step repeats the same backup
+            Jin_np = J_in.numpy()
+
+            def e2e_step():
+                # ONE C-ABI call with host arrays on both sides (pdp_sweep_host): H2D of J_next, the sweep,
+                # D2H of J and pi, pipelined over plane chunks on three streams
+                kernel_eng.sweep_host(Jin_np, Js_np, pis_np)
+        else:
+            def e2e_step():
+                eng.set_J(J_np)             # H2D: J_next planes this rank holds
+                eng.sweep(1)                # sweep (+ halo exchange and stats all-reduce for N>1)
+                kernel_eng.get_J(Js_np)     # D2H: J of the slab
+                kernel_eng.get_pi(pis_np)   # D2H: pi of the slab
         for _ in range(2):
             e2e_step()
         barrier()
@@ -379,8 +389,9 @@ def main():
             dt, h2d, d2h = float(mx[0].item()), float(t[2].item()), float(t[3].item())
         e2e = {"value": evals_per_step * n_e2e / dt, "unit": "evals/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": n_e2e, "ms_per_step": 1e3 * dt / n_e2e,
-               "call": "pdp_set_J + pdp_sweep(1) + pdp_get_J + pdp_get_pi, pinned host buffers"
-                       + (" (per rank: its planes up, its slab down; halo exchange inside)" if world > 1 else "")}
+               "call": ("pdp_sweep_host (H2D J_next -> sweep -> D2H J, pi; chunk-pipelined), pinned host buffers" if world == 1 else
+                        "pdp_set_J + pdp_sweep(1) + pdp_get_J + pdp_get_pi, pinned host buffers "
+                        "(per rank: its planes up, its slab down; halo exchange inside)")}
 
     # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------------------------------
     cpu = cpu_nat = None

@@ -149,6 +149,13 @@ int pdp_sweep(pdp_handle* h, int32_t n_sweeps, pdp_stats* stats_out);
 int pdp_sweep_enqueue(pdp_handle* h);
 int pdp_sweep_collect(pdp_handle* h, pdp_stats* stats_out, int32_t max_out, int32_t* n_out);
 
+/* One sweep with HOST arrays on both sides — the reference's own calling convention, where J_next goes
+ * in as a NumPy array and J, pi come out as NumPy arrays (dynamicprogramming.py:181-236): upload of
+ * J_next (N doubles), backup, download of J (N doubles) and pi (N int64), pipelined over chunks of
+ * axis-0 planes on three streams so that with pinned host buffers both PCIe directions overlap the
+ * kernels.  Single-GPU handles only.  Afterwards the handle is as after pdp_set_J + pdp_sweep(1). */
+int pdp_sweep_host(pdp_handle* h, const double* J_next_host, double* J_host, int64_t* pi_host, pdp_stats* stats_out);
+
 /* LUT mode (system_id == PDP_SYS_LUT): the generic, bit-exact path for arbitrary user systems.
  * x_next: (N_slab, A, n) float64 as discretizer.py:349, G: (N_slab, A) float64 as
  * dynamicprogramming.py:523 (INF already folded in).  Uploaded once, then pdp_sweep() runs

@@ -220,6 +220,11 @@ struct pdp_handle {
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_boundary = nullptr, ev_comm = nullptr;
     long long exchanges = 0;
+    // pdp_sweep_host: copy streams, per-chunk events and statistics
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    std::vector<cudaEvent_t> ev_up, ev_done;
+    cudaEvent_t ev_start = nullptr;
+    double* dchunk_stats = nullptr;
 
     long long slab_nodes() const { return (long long)(slab_end - slab_begin) * plane; }
     long long alloc_nodes() const { return (long long)(alloc_end - alloc_begin) * plane; }
@@ -555,6 +560,12 @@ extern "C" int pdp_destroy(pdp_handle* h) {
     if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
     if (h->ev_boundary) cudaEventDestroy(h->ev_boundary);
     if (h->ev_comm) cudaEventDestroy(h->ev_comm);
+    for (cudaEvent_t e : h->ev_up) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
+    if (h->ev_start) cudaEventDestroy(h->ev_start);
+    if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
+    if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
+    cudaFree(h->dchunk_stats);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -956,6 +967,83 @@ extern "C" int pdp_sweep(pdp_handle* h, int32_t n_sweeps, pdp_stats* stats_out) 
     float ms = 0.f;
     CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->last_ms = ms;
+    return PDP_OK;
+}
+
+// ---- one sweep with HOST arrays on both sides (the reference's own calling convention: J_next is a
+// NumPy array going in, J and pi are NumPy arrays coming out, dynamicprogramming.py:181-236) ----------
+// The grid is cut into chunks of axis-0 planes and the three stages are pipelined on three streams:
+// upload of J_next planes -> backup of a chunk as soon as the planes it can read (chunk + halo) have
+// arrived -> download of the chunk's J and pi while the next chunks compute.  With pinned host
+// buffers the PCIe transfers in both directions overlap the kernels; pageable buffers work but
+// serialise.  Afterwards the handle's state is as after pdp_set_J(J_next) + pdp_sweep(1).
+#define PDP_HOST_MAX_CHUNKS 64
+extern "C" int pdp_sweep_host(pdp_handle* h, const double* J_next_host, double* J_host, int64_t* pi_host, pdp_stats* stats_out) {
+    CHECK_HANDLE(h);
+    if (!J_next_host || !J_host || !pi_host) return fail(h, PDP_EINVAL, "pdp_sweep_host: null pointer");
+    if (h->comm || h->slab_nodes() != h->N) return fail(h, PDP_ESTATE, "pdp_sweep_host: the handle must own the whole grid (single GPU)");
+    if (h->enqueued || h->pending) return fail(h, PDP_ESTATE, "pdp_sweep_host: collect / commit the outstanding sweeps first");
+    int C = 8;
+    if (const char* env = getenv("PYRODP_HOST_CHUNKS")) C = atoi(env);
+    C = std::max(1, std::min(std::min(C, PDP_HOST_MAX_CHUNKS), h->n0));
+    if (!h->h2d_stream) {
+        CUDA_TRY(h, cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
+        CUDA_TRY(h, cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
+        CUDA_TRY(h, cudaMalloc(&h->dchunk_stats, PDP_HOST_MAX_CHUNKS * 3 * sizeof(double)));
+    }
+    while ((int)h->ev_up.size() < C) {
+        cudaEvent_t a = nullptr, b = nullptr;
+        CUDA_TRY(h, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        h->ev_up.push_back(a);
+        CUDA_TRY(h, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        h->ev_done.push_back(b);
+    }
+    std::vector<int> bound(C + 1);
+    for (int i = 0; i <= C; ++i) bound[i] = (int)((long long)i * h->n0 / C);
+    double* Jc = h->dJ[h->cur_idx];
+    double* Jw = h->dJ[1 - h->cur_idx];
+    // uploads start once earlier work of the handle's stream (which may read J[cur]) is done
+    CUDA_TRY(h, cudaEventRecord(h->ev_start, h->stream));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->h2d_stream, h->ev_start, 0));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->d2h_stream, h->ev_start, 0));
+    for (int i = 0; i < C; ++i) {
+        const size_t off = (size_t)bound[i] * h->plane, cnt = (size_t)(bound[i + 1] - bound[i]) * h->plane;
+        if (cnt) CUDA_TRY(h, cudaMemcpyAsync(Jc + off, J_next_host + off, cnt * sizeof(double), cudaMemcpyHostToDevice, h->h2d_stream));
+        CUDA_TRY(h, cudaEventRecord(h->ev_up[i], h->h2d_stream));
+    }
+    h->have_J = true;
+    int waited = -1;  // uploads [0..waited] are already ordered before the compute stream
+    for (int i = 0; i < C; ++i) {
+        // the chunk's backups read planes < bound[i+1] + halo_hi (and > bound[i] - halo_lo: uploaded earlier)
+        const int top = std::min(h->n0, bound[i + 1] + h->halo_hi) - 1;
+        int need = i;
+        while (need + 1 < C && bound[need + 1] <= top) ++need;
+        if (need > waited) { CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_up[need], 0)); waited = need; }
+        int rc = launch_planes(h, bound[i], bound[i + 1], 0, h->dchunk_stats + 3 * i);
+        if (rc != PDP_OK) return rc;
+        CUDA_TRY(h, cudaEventRecord(h->ev_done[i], h->stream));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->d2h_stream, h->ev_done[i], 0));
+        const size_t off = (size_t)bound[i] * h->plane, cnt = (size_t)(bound[i + 1] - bound[i]) * h->plane;
+        if (cnt) {
+            CUDA_TRY(h, cudaMemcpyAsync(J_host + off, Jw + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->d2h_stream));
+            CUDA_TRY(h, cudaMemcpyAsync(pi_host + off, h->dpi + off, cnt * sizeof(long long), cudaMemcpyDeviceToHost, h->d2h_stream));
+        }
+    }
+    double cs[PDP_HOST_MAX_CHUNKS * 3];
+    CUDA_TRY(h, cudaMemcpyAsync(cs, h->dchunk_stats, (size_t)C * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    h->cur_idx = 1 - h->cur_idx;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->d2h_stream));
+    if (stats_out) {
+        pdp_stats s = {cs[0], cs[1], cs[2]};
+        for (int i = 1; i < C; ++i) {
+            s.j_max = std::max(s.j_max, cs[3 * i]);
+            s.delta_max = std::max(s.delta_max, cs[3 * i + 1]);
+            s.delta_min = std::min(s.delta_min, cs[3 * i + 2]);
+        }
+        *stats_out = s;
+    }
     return PDP_OK;
 }
 

@@ -103,16 +103,13 @@ sweep_pendulum_kernel(const __grid_constant__ DevProblem P, const double* __rest
                       double* __restrict__ stats) {
     extern __shared__ __align__(16) double smem[];
     const int N0 = P.dims[0], N1 = P.dims[1], A = P.A;
-    const int N1p = (N1 + 1) & ~1;
-    double* s_lev1 = smem;                       // [N1p]
-    double* s_rinv1 = s_lev1 + N1p;              // [N1p]
-    double2* s_act = (double2*)(s_rinv1 + N1p);  // [A] {t[a] (NaN when isavalidinput fails), du'R du}
+    double2* s_cell = (double2*)smem;   // [N1] {lev[k], 1/(lev[k+1]-lev[k])}: one LDS.128 per cell change
+    double2* s_act = s_cell + N1;       // [A]  {t[a] (NaN when isavalidinput fails), du'R du}
 
     const int i0 = (int)(P.plane_begin + (long long)blockIdx.x);  // row = axis-0 plane
     const double q = __ldg(P.level[0] + i0);
     const double grav = __ldg(P.tab[0] + i0);    // g(q) (pendulum.py:126-137)
-    stage(s_lev1, P.level[1], N1);
-    stage(s_rinv1, P.rinv[1], N1 - 1);
+    for (int i = threadIdx.x; i < N1; i += blockDim.x) s_cell[i] = make_double2(__ldg(P.level[1] + i), __ldg(P.rinv[1] + i));
     for (int i = threadIdx.x; i < A; i += blockDim.x) {
         // ddq = inv(H) . (B u - C dq - g - d), C = 0 (mechanical.py:222-234)
         double t = __ldg(P.bu + i) - grav;
@@ -124,88 +121,106 @@ sweep_pendulum_kernel(const __grid_constant__ DevProblem P, const double* __rest
     const int i1 = (int)(((unsigned)blockIdx.y * SWEEP_THREADS + threadIdx.x) / G);
     const int g = threadIdx.x % G;
     const bool active = i1 < N1;
-    const long long node = (long long)i0 * N1 + i1;
-    Stats3 st = stats_identity();
-    double best = __longlong_as_double(0x7ff0000000000000LL);
+    const long long node = (long long)i0 * N1 + min(i1, N1 - 1);
+    const double PINF = __longlong_as_double(0x7ff0000000000000LL);
+    const double dt = pinned(P.dt);
+    const double dq_node = s_cell[min(i1, N1 - 1)].x;
+
+    // position row of x_next: f[0]*dt + x[0] = dq*dt + q (two roundings, discretizer.py:363)
+    const double xn0 = dq_node * dt + q;
+    // live = this lane evaluates actions.  Dead lanes (past the end of the row, or every action
+    // leaves the box through the position row) still run the loop — the warp votes in it — on an
+    // all-covering dummy cell with zero corner products, and their result is discarded.
+    const bool live = active && !(xn0 < P.lb[0] || xn0 > P.ub[0]);
+    const int c0 = live ? find_cell(P.level[0], N0, xn0, P.lb[0], P.inv_step[0]) : 0;
+    const double lo0 = __ldg(P.level[0] + c0), hi0 = __ldg(P.level[0] + c0 + 1);
+    const double y0 = (xn0 - lo0) / (hi0 - lo0);
+    const double omy0 = 1.0 - y0;
+    const double* __restrict__ row0 = opaque(Jn + (long long)c0 * N1);
+    const double* __restrict__ row1 = opaque(row0 + N1);
+
+    const double dq = live ? dq_node : 0.0;
+    const double Hinv = pinned(P.par[0]);
+    const double damp = P.par[1] * dq;   // d(q,dq) (pendulum.py:141-150)
+
+    // state-only stage cost (costfunction.py:186-197)
+    const double dx[2] = {q - P.xbar[0], dq_node - P.xbar[1]};
+    double gx = 1.0;
+    if (P.cost_id == PDP_COST_QUADRATIC) gx = quad_form<2>(P.Q, dx);
+    const bool ontarget = P.ontarget_check && (norm2<2>(dx) < P.EPS);
+    // g = 0 inside the target zone (costfunction.py:193-197): 0*dt == (gx+gu)*0 == +0
+    const double dt_cost = ontarget ? 0.0 : dt;
+    const double INF = pinned(P.INF), alpha = P.alpha;
+
+    // cached cell of axis 1 and its corner products; live lanes start with an empty cell
+    // (every x fails lo <= x < hi), dead lanes with (-inf, +inf)
+    int c = -1;
+    double lo = live ? PINF : -PINF, hi = -lo, den = 1.0, rinv = 1.0;
+    double p00 = 0.0, p01 = 0.0, p10 = 0.0, p11 = 0.0;
+    double best = PINF;
     int besta = 0x7fffffff;
-    if (active) {
-        const double dq = s_lev1[i1];
-        const double dt = pinned(P.dt);
-
-        // position row of x_next: f[0]*dt + x[0] = dq*dt + q (two roundings, discretizer.py:363)
-        const double xn0 = dq * dt + q;
-        const bool pos_ok = !(xn0 < P.lb[0] || xn0 > P.ub[0]);
-        if (pos_ok) {
-            const int c0 = find_cell(P.level[0], N0, xn0, P.lb[0], P.inv_step[0]);
-            const double lo0 = __ldg(P.level[0] + c0), hi0 = __ldg(P.level[0] + c0 + 1);
-            const double y0 = (xn0 - lo0) / (hi0 - lo0);
-            const double omy0 = 1.0 - y0;
-            const double* __restrict__ row0 = opaque(Jn + (long long)c0 * N1);
-            const double* __restrict__ row1 = opaque(row0 + N1);
-
-            const double Hinv = pinned(P.par[0]);
-            const double damp = P.par[1] * dq;   // d(q,dq) (pendulum.py:141-150)
-
-            // state-only stage cost (costfunction.py:186-197)
-            const double dx[2] = {q - P.xbar[0], dq - P.xbar[1]};
-            double gx = 1.0;
-            if (P.cost_id == PDP_COST_QUADRATIC) gx = quad_form<2>(P.Q, dx);
-            const bool ontarget = P.ontarget_check && (norm2<2>(dx) < P.EPS);
-            // g = 0 inside the target zone (costfunction.py:193-197): 0*dt == (gx+gu)*0 == +0
-            const double dt_cost = ontarget ? 0.0 : dt;
-            const double INF = pinned(P.INF), alpha = P.alpha;
-
-            // cached cell of axis 1 (empty: every x fails lo <= x < hi) and its corner products
-            int c = -1;
-            double lo = __longlong_as_double(0x7ff0000000000000LL), hi = -lo, den = 1.0, rinv = 1.0;
-            double p00 = 0.0, p01 = 0.0, p10 = 0.0, p11 = 0.0;
-#pragma unroll 2
-            for (int a = g; a < A; a += G) {
-                const double2 act = s_act[a];
-                const double xn1 = NODAMP ? (act.x + dq) : ((Hinv * (act.x - damp)) * dt + dq);
-                double Qa;
-                if (!(xn1 >= lo && xn1 < hi)) {
-                    // left the cached cell: isavalidstate (system.py:198-205; a NaN from a disallowed
-                    // action fails it), then the level table decides the cell as scipy's search does
-                    const double lb1 = P.lb[1], ub1 = P.ub[1];
-                    if (!(xn1 >= lb1 && xn1 <= ub1)) {
-                        Qa = INF;
-                        goto compare;
-                    }
+    const int A_up = (G > 1) ? ((A + G - 1) / G) * G : A;  // same trip count for every lane of the warp
+#pragma unroll 4
+    for (int a0 = g; a0 < A_up; a0 += G) {
+        const int a = (G > 1) ? min(a0, A - 1) : a0;
+        const double2 act = s_act[a];
+        const double xn1 = NODAMP ? (act.x + dq) : ((Hinv * (act.x - damp)) * dt + dq);
+        const bool miss = !(xn1 >= lo && xn1 < hi);
+        double Qa;
+        if (__any_sync(0xffffffffu, miss)) {
+            // some lane left its cached cell (rare, and lanes of a row leave together): box test of
+            // isavalidstate (system.py:198-205; a NaN from a disallowed action fails it), then the
+            // level table decides the cell exactly as scipy's search does
+            bool oob = false;
+            if (miss) {
+                const double lb1 = P.lb[1], ub1 = P.ub[1];
+                oob = !(xn1 >= lb1 && xn1 <= ub1);
+                if (!oob) {
                     int k = (c < 0) ? (int)((xn1 - lb1) * P.inv_step[1]) : c + (xn1 >= hi ? 1 : -1);
                     k = min(max(k, 0), N1 - 2);
-                    double l = s_lev1[k], h = s_lev1[k + 1];
-                    if (xn1 >= h || xn1 < l) {
+                    double2 ck = s_cell[k];
+                    double h = s_cell[k + 1].x;
+                    if (xn1 >= h || xn1 < ck.x) {
                         k = min(max((int)((xn1 - lb1) * P.inv_step[1]), 0), N1 - 2);
-                        l = s_lev1[k]; h = s_lev1[k + 1];
-                        while (xn1 < l && k > 0) { --k; h = l; l = s_lev1[k]; }
-                        while (xn1 >= h && k < N1 - 2) { ++k; l = h; h = s_lev1[k + 1]; }
+                        double l = s_cell[k].x;
+                        h = s_cell[k + 1].x;
+                        while (xn1 < l && k > 0) { --k; h = l; l = s_cell[k].x; }
+                        while (xn1 >= h && k < N1 - 2) { ++k; l = h; h = s_cell[k + 1].x; }
+                        ck = s_cell[k];
                     }
-                    c = k; lo = l; hi = h; den = h - l; rinv = s_rinv1[k];
+                    c = k; lo = ck.x; hi = h; den = h - ck.x; rinv = ck.y;
                     const double* __restrict__ r0 = row0 + k;
                     const double* __restrict__ r1 = row1 + k;
                     p00 = __ldg(r0) * omy0; p01 = __ldg(r0 + 1) * omy0;
                     p10 = __ldg(r1) * y0;   p11 = __ldg(r1 + 1) * y0;
                 }
-                {
-                    const double y1 = exact_div(xn1 - lo, den, rinv);
-                    const double omy1 = 1.0 - y1;
-                    // evaluate_linear_2d: value-first association
-                    double Jx = p00 * omy1;
-                    Jx = Jx + p01 * y1;
-                    Jx = Jx + p10 * omy1;
-                    Jx = Jx + p11 * y1;
-                    Qa = (gx + act.y) * dt_cost + (ALPHA1 ? Jx : alpha * Jx);
-                }
-            compare:
-                if (Qa < best) { best = Qa; besta = a; }
             }
-        } else if (g == 0) {
-            best = P.INF;  // every action leaves the box: Q = INF for all, argmin = 0
-            besta = 0;
+            const double y1 = exact_div(xn1 - lo, den, rinv);
+            const double omy1 = 1.0 - y1;
+            double Jx = p00 * omy1;
+            Jx = Jx + p01 * y1;
+            Jx = Jx + p10 * omy1;
+            Jx = Jx + p11 * y1;
+            Qa = (gx + act.y) * dt_cost + (ALPHA1 ? Jx : alpha * Jx);
+            if (oob) Qa = INF;
+        } else {
+            const double y1 = exact_div(xn1 - lo, den, rinv);
+            const double omy1 = 1.0 - y1;
+            // evaluate_linear_2d: value-first association
+            double Jx = p00 * omy1;
+            Jx = Jx + p01 * y1;
+            Jx = Jx + p10 * omy1;
+            Jx = Jx + p11 * y1;
+            Qa = (gx + act.y) * dt_cost + (ALPHA1 ? Jx : alpha * Jx);
         }
+        if ((G == 1 || a0 < A) && Qa < best) { best = Qa; besta = a; }
+    }
+    if (!live) {  // every action leaves the box: Q = INF for all, argmin = 0
+        best = (g == 0) ? P.INF : PINF;
+        besta = (g == 0) ? 0 : 0x7fffffff;
     }
     if (G > 1) lane_group_argmin(best, besta, G);
+    Stats3 st = stats_identity();
     if (active && g == 0) {
         if (besta == 0x7fffffff) besta = 0;  // no Q below +inf (cf.INF = inf): np.argmin of a constant row is 0
         Jo[node] = best;
@@ -221,102 +236,19 @@ sweep_pendulum_kernel(const __grid_constant__ DevProblem P, const double* __rest
 // manipulator.py:795 TwoLinkManipulator) and cart-pole (cartpole.py:322)
 // grid: blockIdx.x = (i0,i1) plane of the slab, blockIdx.y = chunk of the (i2,i3) plane
 //
-// The 16-corner blend is a chain of 16 dependent FP64 adds in the reference's association
-// (_rgi.py:528-547), so one eval exposes little instruction-level parallelism and the FP64 pipe
-// idles on its own latency (ncu r01b: pipe 47 % busy, "wait" the top stall).  Each thread therefore
-// works on ILP actions at a time: their cells are located one after the other (register-cached
-// cell, table-checked), then the ILP blends run as one straight-line block that the scheduler
-// interleaves.  The box test of isavalidstate is folded into the cell test: a hit in the cached
-// cell proves lb <= x <= ub.
+// Measured alternatives that did NOT pay (profiles/r01h_variants.txt): two actions per iteration with
+// interleaved 16-corner blends (more registers, fewer resident warps, the L1 data pipe — ~65
+// wavefronts per warp-eval for the 16 gathers — is the co-limiter, not FP64 latency), and folding the
+// box test into the cell test (the out-of-box evals that dominate the 2-input systems got dearer).
 // =================================================================================================
 #ifndef MECH2_MIN_BLOCKS
-#define MECH2_MIN_BLOCKS 3
+#define MECH2_MIN_BLOCKS 4
 #endif
-#ifndef MECH2_ILP
-#define MECH2_ILP 2
-#endif
-
-struct Cell {
-    int c;
-    double lo, hi, den, rinv;
-};
-
-__device__ __forceinline__ void cell_set(Cell& k, const double* __restrict__ s_lev, const double* __restrict__ s_rinv,
-                                         int nlev, int guess) {
-    k.c = min(max(guess, 0), nlev - 2);
-    k.lo = s_lev[k.c];
-    k.hi = s_lev[k.c + 1];
-    k.den = k.hi - k.lo;
-    k.rinv = s_rinv[k.c];
-}
-
-// Position the cell so that lev[c] <= x < lev[c+1] (last cell closed on the right) — the interval
-// scipy's find_interval_ascending returns; false when x is outside [lb, ub] (or NaN), i.e. when
-// isavalidstate fails (system.py:198-205).  Fast paths: cached cell, neighbouring cell; otherwise an
-// arithmetic guess followed by a table-checked walk.
-__device__ __forceinline__ bool cell_locate(Cell& k, const double* __restrict__ s_lev, const double* __restrict__ s_rinv,
-                                            int nlev, double x, double lb, double ub, double inv_step) {
-    if (x >= k.lo && x < k.hi) return true;
-    if (!(x >= lb && x <= ub)) return false;
-    int c = min(max(k.c + (x >= k.hi ? 1 : -1), 0), nlev - 2);
-    double lo = s_lev[c], hi = s_lev[c + 1];
-    if (x >= hi || x < lo) {
-        c = min(max((int)((x - lb) * inv_step), 0), nlev - 2);
-        lo = s_lev[c]; hi = s_lev[c + 1];
-        while (x < lo && c > 0) { --c; hi = lo; lo = s_lev[c]; }
-        while (x >= hi && c < nlev - 2) { ++c; lo = hi; hi = s_lev[c + 1]; }
-    }
-    k.c = c; k.lo = lo; k.hi = hi; k.den = hi - lo;
-    k.rinv = s_rinv[c];
-    return true;
-}
-
-// _evaluate_linear (_rgi.py:520-549) for one query: corners in itertools.product order (axis 0
-// slowest, offset 0 before 1), weight-first association w = (((1*w0)*w1)*w2)*w3, value = 0 + sum.
-// w00..w11 are the action-independent (w0*w1) products.
-__device__ __forceinline__ double blend16(const double* __restrict__ b00, const double* __restrict__ b01,
-                                          const double* __restrict__ b10, const double* __restrict__ b11, int o, int N3,
-                                          double w00, double w01, double w10, double w11, double y2, double y3) {
-    const double omy2 = 1.0 - y2, omy3 = 1.0 - y3;
-    const int o2 = o + N3;
-    double Jx;
-    {
-        const double wa = w00 * omy2, wb = w00 * y2;
-        Jx = 0.0 + __ldg(b00 + o) * (wa * omy3);
-        Jx = Jx + __ldg(b00 + o + 1) * (wa * y3);
-        Jx = Jx + __ldg(b00 + o2) * (wb * omy3);
-        Jx = Jx + __ldg(b00 + o2 + 1) * (wb * y3);
-    }
-    {
-        const double wa = w01 * omy2, wb = w01 * y2;
-        Jx = Jx + __ldg(b01 + o) * (wa * omy3);
-        Jx = Jx + __ldg(b01 + o + 1) * (wa * y3);
-        Jx = Jx + __ldg(b01 + o2) * (wb * omy3);
-        Jx = Jx + __ldg(b01 + o2 + 1) * (wb * y3);
-    }
-    {
-        const double wa = w10 * omy2, wb = w10 * y2;
-        Jx = Jx + __ldg(b10 + o) * (wa * omy3);
-        Jx = Jx + __ldg(b10 + o + 1) * (wa * y3);
-        Jx = Jx + __ldg(b10 + o2) * (wb * omy3);
-        Jx = Jx + __ldg(b10 + o2 + 1) * (wb * y3);
-    }
-    {
-        const double wa = w11 * omy2, wb = w11 * y2;
-        Jx = Jx + __ldg(b11 + o) * (wa * omy3);
-        Jx = Jx + __ldg(b11 + o + 1) * (wa * y3);
-        Jx = Jx + __ldg(b11 + o2) * (wb * omy3);
-        Jx = Jx + __ldg(b11 + o2 + 1) * (wb * y3);
-    }
-    return Jx;
-}
-
 template <int SYS, int G, bool ALPHA1>
 __global__ void __launch_bounds__(SWEEP_THREADS, MECH2_MIN_BLOCKS)
 sweep_mech2_kernel(const __grid_constant__ DevProblem P, const double* __restrict__ Jn, double* __restrict__ Jo,
                    long long* __restrict__ pi, unsigned long long* __restrict__ partials, unsigned int* counter,
                    double* __restrict__ stats) {
-    constexpr int ILP = MECH2_ILP;
     extern __shared__ __align__(16) double smem[];
     const int N0 = P.dims[0], N1 = P.dims[1], N2 = P.dims[2], N3 = P.dims[3], A = P.A;
     const int N2p = (N2 + 1) & ~1, N3p = (N3 + 1) & ~1;
@@ -404,56 +336,60 @@ sweep_mech2_kernel(const __grid_constant__ DevProblem P, const double* __restric
             const double is2 = P.inv_step[2], is3 = P.inv_step[3];
             const double INF = P.INF, alpha = P.alpha;
             const double dt_cost = ontarget ? 0.0 : dt;
-            Cell k2, k3;
-            cell_set(k2, s_lev2, s_rinv2, N2, i2);
-            cell_set(k3, s_lev3, s_rinv3, N3, i3);
-            for (int a0 = g; a0 < A; a0 += ILP * G) {
-                bool ok[ILP];
-                int off[ILP];
-                double y2[ILP], y3[ILP], gua[ILP];
-#pragma unroll
-                for (int j = 0; j < ILP; ++j) {
-                    // the tail of the action list re-evaluates its last action; the result is not used
-                    const int a = min(a0 + j * G, A - 1);
-                    const double2 bu = s_act[2 * a];
-                    gua[j] = s_act[2 * a + 1].x;
-                    // B u - C dq - g - d, left to right (mechanical.py:231).  For the cart-pole g[0], d[0]
-                    // and d[1] are literal zeros (cartpole.py:415-437) and x - 0.0 == x bit for bit.
-                    const double r0 = (SYS == PDP_SYS_CARTPOLE) ? (bu.x - cd0) : (((bu.x - cd0) - g0) - d0);
-                    const double r1 = (SYS == PDP_SYS_CARTPOLE) ? ((bu.y - cd1) - g1) : (((bu.y - cd1) - g1) - d1);
-                    const double ddq0 = mv2(H00, H01, r0, r1);
-                    const double ddq1 = mv2(H10, H11, r0, r1);
-                    const double xn2 = ddq0 * dt + dq0;
-                    const double xn3 = ddq1 * dt + dq1;
-                    ok[j] = cell_locate(k2, s_lev2, s_rinv2, N2, xn2, lb2, ub2, is2) &&
-                            cell_locate(k3, s_lev3, s_rinv3, N3, xn3, lb3, ub3, is3);
-                    y2[j] = exact_div(xn2 - k2.lo, k2.den, k2.rinv);
-                    y3[j] = exact_div(xn3 - k3.lo, k3.den, k3.rinv);
-                    off[j] = k2.c * N3 + k3.c;
-                }
-                double Jx[ILP];
-                bool all_ok = true;
-#pragma unroll
-                for (int j = 0; j < ILP; ++j) all_ok = all_ok && ok[j];
-                if (all_ok) {
-                    // one straight-line block: the ILP dependent add chains interleave
-#pragma unroll
-                    for (int j = 0; j < ILP; ++j)
-                        Jx[j] = blend16(b00, b01, b10, b11, off[j], N3, w00, w01, w10, w11, y2[j], y3[j]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < ILP; ++j) {
-                        Jx[j] = 0.0;
-                        if (ok[j]) Jx[j] = blend16(b00, b01, b10, b11, off[j], N3, w00, w01, w10, w11, y2[j], y3[j]);
+            CellCache k2, k3;
+            cell_init(k2, s_lev2, s_rinv2, N2, i2);
+            cell_init(k3, s_lev3, s_rinv3, N3, i3);
+            for (int a = g; a < A; a += G) {
+                const double2 bu = s_act[2 * a];
+                // B u - C dq - g - d, left to right (mechanical.py:231).  For the cart-pole g[0], d[0]
+                // and d[1] are literal zeros (cartpole.py:415-437) and x - 0.0 == x bit for bit.
+                const double r0 = (SYS == PDP_SYS_CARTPOLE) ? (bu.x - cd0) : (((bu.x - cd0) - g0) - d0);
+                const double r1 = (SYS == PDP_SYS_CARTPOLE) ? ((bu.y - cd1) - g1) : (((bu.y - cd1) - g1) - d1);
+                const double ddq0 = mv2(H00, H01, r0, r1);
+                const double ddq1 = mv2(H10, H11, r0, r1);
+                const double xn2 = ddq0 * dt + dq0;
+                const double xn3 = ddq1 * dt + dq1;
+                double Qa = INF;
+                if (xn2 >= lb2 && xn2 <= ub2 && xn3 >= lb3 && xn3 <= ub3) {
+                    cell_seek(k2, s_lev2, s_rinv2, N2, xn2, lb2, is2);
+                    cell_seek(k3, s_lev3, s_rinv3, N3, xn3, lb3, is3);
+                    const double y2 = exact_div(xn2 - k2.lo, k2.hi - k2.lo, k2.rinv);
+                    const double y3 = exact_div(xn3 - k3.lo, k3.hi - k3.lo, k3.rinv);
+                    const double omy2 = 1.0 - y2, omy3 = 1.0 - y3;
+                    const int o = k2.c * N3 + k3.c;
+                    const int o2 = o + N3;
+                    double Jx;
+                    {   // corners in itertools.product order: axis 0 slowest, offset 0 before 1
+                        const double wa = w00 * omy2, wb = w00 * y2;
+                        Jx = 0.0 + __ldg(b00 + o) * (wa * omy3);  // value = 0 + term (_rgi.py:528,547)
+                        Jx = Jx + __ldg(b00 + o + 1) * (wa * y3);
+                        Jx = Jx + __ldg(b00 + o2) * (wb * omy3);
+                        Jx = Jx + __ldg(b00 + o2 + 1) * (wb * y3);
                     }
+                    {
+                        const double wa = w01 * omy2, wb = w01 * y2;
+                        Jx = Jx + __ldg(b01 + o) * (wa * omy3);
+                        Jx = Jx + __ldg(b01 + o + 1) * (wa * y3);
+                        Jx = Jx + __ldg(b01 + o2) * (wb * omy3);
+                        Jx = Jx + __ldg(b01 + o2 + 1) * (wb * y3);
+                    }
+                    {
+                        const double wa = w10 * omy2, wb = w10 * y2;
+                        Jx = Jx + __ldg(b10 + o) * (wa * omy3);
+                        Jx = Jx + __ldg(b10 + o + 1) * (wa * y3);
+                        Jx = Jx + __ldg(b10 + o2) * (wb * omy3);
+                        Jx = Jx + __ldg(b10 + o2 + 1) * (wb * y3);
+                    }
+                    {
+                        const double wa = w11 * omy2, wb = w11 * y2;
+                        Jx = Jx + __ldg(b11 + o) * (wa * omy3);
+                        Jx = Jx + __ldg(b11 + o + 1) * (wa * y3);
+                        Jx = Jx + __ldg(b11 + o2) * (wb * omy3);
+                        Jx = Jx + __ldg(b11 + o2 + 1) * (wb * y3);
+                    }
+                    Qa = (gx + s_act[2 * a + 1].x) * dt_cost + (ALPHA1 ? Jx : alpha * Jx);
                 }
-#pragma unroll
-                for (int j = 0; j < ILP; ++j) {
-                    const int a = a0 + j * G;
-                    const double Qv = (gx + gua[j]) * dt_cost + (ALPHA1 ? Jx[j] : alpha * Jx[j]);
-                    const double Qa = ok[j] ? Qv : INF;
-                    if (a < A && Qa < best) { best = Qa; besta = a; }
-                }
+                if (Qa < best) { best = Qa; besta = a; }
             }
         } else if (g == 0) {
             best = P.INF;
@@ -462,7 +398,7 @@ sweep_mech2_kernel(const __grid_constant__ DevProblem P, const double* __restric
     }
     if (G > 1) lane_group_argmin(best, besta, G);
     if (active && g == 0) {
-        if (besta == 0x7fffffff) besta = 0;
+        if (besta == 0x7fffffff) besta = 0;  // no Q below +inf (cf.INF = inf): np.argmin of a constant row is 0
         Jo[node] = best;
         pi[node] = besta;
         const double d = best - Jn[node];

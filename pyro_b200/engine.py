@@ -85,6 +85,17 @@ class Engine:
         self._ck(self.lib.pdp_sweep(self.h, int(n_sweeps), stats.ctypes.data))
         return stats
 
+    def sweep_host(self, J_next, J_out=None, pi_out=None):
+        """One sweep with host arrays on both sides (upload, backup and download pipelined over plane
+        chunks): returns (J, pi, [j_max, delta_max, delta_min]).  Pinned buffers overlap the copies."""
+        J_next = np.ascontiguousarray(J_next, dtype=np.float64)
+        if J_next.size != self.N:
+            raise ValueError("Grid size does not match data")
+        J_out, pi_out = self._out(J_out, np.float64), self._out(pi_out, np.int64)
+        stats = np.empty(3, dtype=np.float64)
+        self._ck(self.lib.pdp_sweep_host(self.h, J_next.ctypes.data, J_out.ctypes.data, pi_out.ctypes.data, stats.ctypes.data))
+        return J_out, pi_out, stats
+
     def sweep_nowait(self):
         """Enqueue one sweep (+ exchange when a communicator is attached) without blocking."""
         self._ck(self.lib.pdp_sweep_enqueue(self.h))

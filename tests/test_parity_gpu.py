@@ -241,3 +241,47 @@ def test_exact_div_equals_ieee_division():
     assert rc == 0
     assert np.array_equal(qi, a / den)
     assert np.array_equal(qf, qi)
+
+
+@pytest.mark.parametrize("lanes", [1, 4, 16])
+@pytest.mark.parametrize("name", ["pend_101x101x21", "pend_time_41x61x7", "dpend_example", "twolink_soft", "cartpole_swingup"])
+def test_every_lane_split_matches_goldens(name, lanes, monkeypatch):
+    """G lanes per node (1: a thread scans all actions; 4 / 16: shuffle argmin with np.argmin's first-index rule):
+    every instantiation must reproduce the reference fixtures, whatever the grid size picks by default."""
+    monkeypatch.setenv("PYRODP_LANES", str(lanes))
+    case, gold = CASES[name], load_golden(name)
+    _, grid, cf = build_case(case)
+    eng = Engine(problem.extract(grid, cf, case.get("alpha", 1.0)))
+    assert eng.lanes_per_node == lanes
+    eng.set_J(gold["J0"])
+    k = case["snapshots"][1]
+    eng.sweep(k)
+    assert np.array_equal(eng.get_J(), gold[f"J_{k}"]) and np.array_equal(eng.get_pi(), gold[f"pi_{k}"])
+    eng.close()
+
+
+@pytest.mark.parametrize("chunks", [1, 3, 8, 64])
+@pytest.mark.parametrize("name", ["pend_301", "cartpole_25", "dpend_21"])
+def test_host_array_sweep_is_the_same_backup(name, chunks, monkeypatch):
+    """pdp_sweep_host (host arrays in/out, chunk-pipelined copies) == pdp_set_J + pdp_sweep + getters, for any
+    chunking (a chunk's backups read its halo planes, which must have been uploaded before it runs)."""
+    monkeypatch.setenv("PYRODP_HOST_CHUNKS", str(chunks))
+    case = MID[name]
+    _, grid, cf = build_case(case)
+    P = problem.extract(grid, cf, case.get("alpha", 1.0))
+    eng = Engine(P)
+    J0 = np.random.default_rng(3).uniform(0, 300, P.N)
+    eng.set_J(J0)
+    st_ref = eng.sweep(1)
+    J_ref, pi_ref = eng.get_J(), eng.get_pi()
+    eng.set_J(np.zeros(P.N))              # make sure the result really comes from the uploaded array
+    J, pi, st = eng.sweep_host(J0)
+    assert np.array_equal(J, J_ref) and np.array_equal(pi, pi_ref) and np.array_equal(st, st_ref[0])
+    assert np.array_equal(eng.get_J(), J_ref) and np.array_equal(eng.get_J_next(), J0) and np.array_equal(eng.get_pi(), pi_ref)
+    J2, pi2, _ = eng.sweep_host(J)        # chained: second backup equals sweeping on
+    eng.set_J(J0)
+    eng.sweep(2)
+    assert np.array_equal(J2, eng.get_J()) and np.array_equal(pi2, eng.get_pi())
+    with pytest.raises(ValueError):
+        eng.sweep_host(J0[:-1])
+    eng.close()
