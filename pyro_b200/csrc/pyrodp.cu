@@ -211,6 +211,8 @@ struct pdp_handle {
     size_t smem_bytes = 0;
     int lanes_per_node = 1;       // G of the fused kernels
     int force_lanes = 0;          // test hook (PYRODP_LANES): pin G to 1, 4 or 16
+    bool pend_mono = false;       // pendulum: x_next[1] is non-decreasing along the action list (see sweep_fused.cuh, MONO)
+    bool force_generic = false;   // test hook (PYRODP_GENERIC=1): use the order-agnostic action loop anyway
     void* fused = nullptr;        // selected fused kernel instantiation
     // multi-GPU (one process per GPU): NCCL communicator, side stream for the halo exchange
     void* comm = nullptr;
@@ -302,9 +304,11 @@ static int expected_tab_len(const pdp_problem* p, int t, long long* len) {
 typedef void (*fused_kernel_t)(const DevProblem, const double*, double*, long long*, unsigned long long*, unsigned int*, double*);
 
 template <int G, bool A1>
-static fused_kernel_t fused_for(int system_id, bool nodamp) {
+static fused_kernel_t fused_for(int system_id, bool nodamp, bool mono) {
     switch (system_id) {
-        case PDP_SYS_PENDULUM: return nodamp ? sweep_pendulum_kernel<G, A1, true> : sweep_pendulum_kernel<G, A1, false>;
+        case PDP_SYS_PENDULUM:
+            if (mono) return nodamp ? sweep_pendulum_kernel<G, A1, true, true> : sweep_pendulum_kernel<G, A1, false, true>;
+            return nodamp ? sweep_pendulum_kernel<G, A1, true, false> : sweep_pendulum_kernel<G, A1, false, false>;
         case PDP_SYS_TWOLINK: return sweep_mech2_kernel<PDP_SYS_TWOLINK, G, A1>;
         case PDP_SYS_CARTPOLE: return sweep_mech2_kernel<PDP_SYS_CARTPOLE, G, A1>;
     }
@@ -326,16 +330,17 @@ static int select_fused_kernel(pdp_handle* h) {
     const bool a1 = P.alpha_is_one != 0;
     fused_kernel_t k = nullptr;
     const bool nd = (P.system_id == PDP_SYS_PENDULUM) && P.par[1] == 0.0;  // d1 == 0: no damping term
-    if (G == 1) k = a1 ? fused_for<1, true>(P.system_id, nd) : fused_for<1, false>(P.system_id, nd);
-    else if (G == 4) k = a1 ? fused_for<4, true>(P.system_id, nd) : fused_for<4, false>(P.system_id, nd);
-    else k = a1 ? fused_for<16, true>(P.system_id, nd) : fused_for<16, false>(P.system_id, nd);
+    const bool mono = h->pend_mono && !h->force_generic;
+    if (G == 1) k = a1 ? fused_for<1, true>(P.system_id, nd, mono) : fused_for<1, false>(P.system_id, nd, mono);
+    else if (G == 4) k = a1 ? fused_for<4, true>(P.system_id, nd, mono) : fused_for<4, false>(P.system_id, nd, mono);
+    else k = a1 ? fused_for<16, true>(P.system_id, nd, mono) : fused_for<16, false>(P.system_id, nd, mono);
     if (!k) return fail(h, PDP_ENOTSUP, "no fused kernel for this system");
     h->lanes_per_node = G;
     h->fused = (void*)k;
     const size_t A = (size_t)P.A;
     if (P.system_id == PDP_SYS_PENDULUM) {
         const size_t n1p = (size_t)((P.dims[1] + 1) & ~1);
-        h->smem_bytes = (2 * n1p + 2 * A) * sizeof(double) + 16;
+        h->smem_bytes = (2 * n1p + 2 * (A + 2 * (size_t)G)) * sizeof(double) + 16;  // {level, 1/step} records + padded action records
         if (h->N > 0x7fffffffLL) return fail(h, PDP_ENOTSUP, "2-D grids are limited to 2^31-1 nodes");
         if (((long long)P.dims[1] * G + SWEEP_THREADS - 1) / SWEEP_THREADS > 65535)
             return fail(h, PDP_ENOTSUP, "grid too large for one launch (dims[1] too big)");
@@ -440,6 +445,7 @@ extern "C" int pdp_create(const pdp_problem* p, pdp_handle** out) {
     auto bail = [&](int code) { pdp_destroy(h); return code; };
     if (cudaGetDevice(&h->device) != cudaSuccess) { g_err = "cudaGetDevice failed"; return bail(PDP_ECUDA); }
     if (const char* env = getenv("PYRODP_LANES")) h->force_lanes = atoi(env);
+    if (const char* env = getenv("PYRODP_GENERIC")) h->force_generic = atoi(env) != 0;
 
     DevProblem& P = h->P;
     P.n = p->n; P.m = p->m; P.dof = p->n / 2; P.A = (int)A;
@@ -512,6 +518,13 @@ extern "C" int pdp_create(const pdp_problem* p, pdp_handle** out) {
                 P.all_act_ok = 0;
                 for (int d = 0; d < P.dof; ++d) bu[(size_t)a * P.dof + d] = __builtin_nan("");
             }
+        if (p->system_id == PDP_SYS_PENDULUM) {
+            // x_next[1] = ((B.u - g - d) * inv(H)) * dt + dq is a chain of monotone IEEE operations of B.u when
+            // inv(H) > 0 and dt > 0: ascending B.u (and no disallowed action) => non-decreasing x_next[1]
+            bool asc = P.all_act_ok && p->sys_par[0] > 0.0 && p->dt > 0.0;
+            for (long long a = 1; a < A && asc; ++a) asc = bu[a] >= bu[a - 1];
+            h->pend_mono = asc;
+        }
         if ((rc = upload(h, bu.data(), bu.size(), &P.bu)) != PDP_OK) return bail(rc);
         if ((rc = upload(h, p->gu, (size_t)A, &P.gu)) != PDP_OK) return bail(rc);
         if ((rc = upload(h, (const unsigned char*)p->act_ok, (size_t)A, &P.act_ok)) != PDP_OK) return bail(rc);

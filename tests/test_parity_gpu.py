@@ -108,8 +108,9 @@ MID = {
 
 
 @pytest.mark.parametrize("name", list(MID))
-def test_mid_size_random_J_equals_c_oracle(name):
+def test_mid_size_random_J_equals_c_oracle(name, monkeypatch, generic=0):
     """Sizes the reference cannot build in reasonable time; rough (random) J so every corner weight matters."""
+    monkeypatch.setenv("PYRODP_GENERIC", str(generic))
     case = MID[name]
     _, grid, cf = build_case(case)
     P = problem.extract(grid, cf, case.get("alpha", 1.0))
@@ -126,6 +127,29 @@ def test_mid_size_random_J_equals_c_oracle(name):
     d = J2 - J1
     assert stats[1, 0] == J2.max() and stats[1, 1] == d.max() and stats[1, 2] == d.min()
     eng.close()
+
+
+def test_pendulum_order_agnostic_loop_on_mid_size_and_descending_inputs(monkeypatch):
+    """The generic pendulum loop (any action order): forced on an ascending grid, and selected by the library
+    itself when B.u is not ascending (here: the descriptor's per-action tables reversed and shuffled)."""
+    test_mid_size_random_J_equals_c_oracle("pend_301", monkeypatch, generic=1)
+    monkeypatch.setenv("PYRODP_GENERIC", "0")
+    case = dict(system="SinglePendulum", x_grid_dim=[65, 77], u_grid_dim=[23], xbar=[-3.14, 0.0], INF=300.0,
+                u_lb=[-8.0], u_ub=[8.0], sys_params={"d1": 0.2})
+    _, grid, cf = build_case(case)
+    for order in ("descending", "shuffled"):
+        P = problem.extract(grid, cf, 1.0)
+        perm = np.arange(P.A)[::-1] if order == "descending" else np.random.default_rng(11).permutation(P.A)
+        # the per-action tables of the descriptor (B.u, du'R du) in another order: engine and oracle read the same bytes
+        P.tables["bu"][:] = P.tables["bu"][perm]
+        P.tables["gu"][:] = P.tables["gu"][perm]
+        eng = Engine(P)
+        J0 = np.random.default_rng(5).uniform(0, 300, P.N)
+        eng.set_J(J0)
+        eng.sweep(1)
+        J1, pi1 = c_oracle.sweep_fused(P, J0)
+        assert np.array_equal(eng.get_J(), J1) and np.array_equal(eng.get_pi(), pi1), order
+        eng.close()
 
 
 def test_full_size_config2_sampled_against_oracle_and_properties():
@@ -243,12 +267,17 @@ def test_exact_div_equals_ieee_division():
     assert np.array_equal(qf, qi)
 
 
+@pytest.mark.parametrize("generic", [0, 1])
 @pytest.mark.parametrize("lanes", [1, 4, 16])
-@pytest.mark.parametrize("name", ["pend_101x101x21", "pend_time_41x61x7", "dpend_example", "twolink_soft", "cartpole_swingup"])
-def test_every_lane_split_matches_goldens(name, lanes, monkeypatch):
-    """G lanes per node (1: a thread scans all actions; 4 / 16: shuffle argmin with np.argmin's first-index rule):
-    every instantiation must reproduce the reference fixtures, whatever the grid size picks by default."""
+@pytest.mark.parametrize("name", ["pend_51x51x11", "pend_101x101x21", "pend_time_41x61x7", "dpend_example", "twolink_soft", "cartpole_swingup"])
+def test_every_lane_split_matches_goldens(name, lanes, generic, monkeypatch):
+    """G lanes per node (1: a thread scans all actions; 4 / 16: shuffle argmin with np.argmin's first-index rule),
+    and for the pendulum both action loops (the one that exploits an ascending input grid and the
+    order-agnostic one): every instantiation must reproduce the reference fixtures."""
+    if generic and not name.startswith("pend"):
+        pytest.skip("only the pendulum kernel has two action loops")
     monkeypatch.setenv("PYRODP_LANES", str(lanes))
+    monkeypatch.setenv("PYRODP_GENERIC", str(generic))
     case, gold = CASES[name], load_golden(name)
     _, grid, cf = build_case(case)
     eng = Engine(problem.extract(grid, cf, case.get("alpha", 1.0)))
