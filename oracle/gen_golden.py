@@ -19,7 +19,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import ref_loader  # noqa: E402
-from tests.cases import CASES  # noqa: E402
+from tests.cases import CASES, POLICY_CASES, LinearFeedback  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -76,5 +76,28 @@ def main():
               f"J_max={dp.J.max():.6f} -> {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def main_policy():
+    """Fixtures of the reference's PolicyEvaluatorWithLookUpTable (dynamicprogramming.py:677-752)."""
+    ns = ref_loader.load()
+    for name, case in POLICY_CASES.items():
+        with ref_loader.quiet():
+            sys_, grid, cf, _ = build_reference(ns, case)
+            ctl = LinearFeedback(**case["ctl"])
+            pe = ns.dynamicprogramming.PolicyEvaluatorWithLookUpTable(ctl, grid, cf)
+            pe.alpha = case.get("alpha", 1.0)
+            out = {"case": json.dumps(case), "J0": pe.J.copy(), "x_next_table": pe.x_next_table.copy(), "G": pe.G.copy()}
+            k = 0
+            for target in case["snapshots"]:
+                pe.compute_steps(target - k)
+                k = target
+                out[f"J_{k}"] = pe.J.copy()
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(f"{name}: N={grid.nodes_n} snapshots={case['snapshots']} J_max={pe.J.max():.6f} "
+              f"INF nodes={int((pe.G == cf.INF).sum())} -> {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 if __name__ == "__main__":
-    main()
+    if "--policy-only" not in sys.argv:
+        main()
+    main_policy()

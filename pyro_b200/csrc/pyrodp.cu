@@ -224,6 +224,8 @@ struct pdp_handle {
     long long exchanges = 0;
     // pdp_sweep_host: copy streams, per-chunk events and statistics
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaStream_t side_stream[2] = {nullptr, nullptr};  // chunk kernels rotate over {stream, side_stream[0], side_stream[1]}
+    cudaEvent_t ev_side[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> ev_up, ev_done;
     cudaEvent_t ev_start = nullptr;
     double* dchunk_stats = nullptr;
@@ -576,6 +578,10 @@ extern "C" int pdp_destroy(pdp_handle* h) {
     for (cudaEvent_t e : h->ev_up) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
     if (h->ev_start) cudaEventDestroy(h->ev_start);
+    for (int i = 0; i < 2; ++i) {
+        if (h->side_stream[i]) cudaStreamDestroy(h->side_stream[i]);
+        if (h->ev_side[i]) cudaEventDestroy(h->ev_side[i]);
+    }
     if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
     if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     cudaFree(h->dchunk_stats);
@@ -1004,6 +1010,10 @@ extern "C" int pdp_sweep_host(pdp_handle* h, const double* J_next_host, double* 
         CUDA_TRY(h, cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
         CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
         CUDA_TRY(h, cudaMalloc(&h->dchunk_stats, PDP_HOST_MAX_CHUNKS * 3 * sizeof(double)));
+        for (int i = 0; i < 2; ++i) {
+            CUDA_TRY(h, cudaStreamCreateWithFlags(&h->side_stream[i], cudaStreamNonBlocking));
+            CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_side[i], cudaEventDisableTiming));
+        }
     }
     while ((int)h->ev_up.size() < C) {
         cudaEvent_t a = nullptr, b = nullptr;
@@ -1020,22 +1030,29 @@ extern "C" int pdp_sweep_host(pdp_handle* h, const double* J_next_host, double* 
     CUDA_TRY(h, cudaEventRecord(h->ev_start, h->stream));
     CUDA_TRY(h, cudaStreamWaitEvent(h->h2d_stream, h->ev_start, 0));
     CUDA_TRY(h, cudaStreamWaitEvent(h->d2h_stream, h->ev_start, 0));
+    // The chunk backups are independent of each other (all read J[cur], each writes its own planes), so they
+    // rotate over three streams with their own statistics scratch: a chunk that cannot fill the 148 SMs
+    // shares them with the next one instead of leaving a partial wave behind.
+    cudaStream_t cs[3] = {h->stream, h->side_stream[0], h->side_stream[1]};
+    const int K = std::min(3, C);
+    for (int i = 1; i < K; ++i) CUDA_TRY(h, cudaStreamWaitEvent(cs[i], h->ev_start, 0));
     for (int i = 0; i < C; ++i) {
         const size_t off = (size_t)bound[i] * h->plane, cnt = (size_t)(bound[i + 1] - bound[i]) * h->plane;
         if (cnt) CUDA_TRY(h, cudaMemcpyAsync(Jc + off, J_next_host + off, cnt * sizeof(double), cudaMemcpyHostToDevice, h->h2d_stream));
         CUDA_TRY(h, cudaEventRecord(h->ev_up[i], h->h2d_stream));
     }
     h->have_J = true;
-    int waited = -1;  // uploads [0..waited] are already ordered before the compute stream
+    int waited[3] = {-1, -1, -1};  // uploads [0..waited] are already ordered before that compute stream
     for (int i = 0; i < C; ++i) {
         // the chunk's backups read planes < bound[i+1] + halo_hi (and > bound[i] - halo_lo: uploaded earlier)
         const int top = std::min(h->n0, bound[i + 1] + h->halo_hi) - 1;
         int need = i;
         while (need + 1 < C && bound[need + 1] <= top) ++need;
-        if (need > waited) { CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_up[need], 0)); waited = need; }
-        int rc = launch_planes(h, bound[i], bound[i + 1], 0, h->dchunk_stats + 3 * i);
+        const int si = i % K;
+        if (need > waited[si]) { CUDA_TRY(h, cudaStreamWaitEvent(cs[si], h->ev_up[need], 0)); waited[si] = need; }
+        int rc = launch_planes(h, bound[i], bound[i + 1], si, h->dchunk_stats + 3 * i, cs[si]);
         if (rc != PDP_OK) return rc;
-        CUDA_TRY(h, cudaEventRecord(h->ev_done[i], h->stream));
+        CUDA_TRY(h, cudaEventRecord(h->ev_done[i], cs[si]));
         CUDA_TRY(h, cudaStreamWaitEvent(h->d2h_stream, h->ev_done[i], 0));
         const size_t off = (size_t)bound[i] * h->plane, cnt = (size_t)(bound[i + 1] - bound[i]) * h->plane;
         if (cnt) {
@@ -1043,17 +1060,21 @@ extern "C" int pdp_sweep_host(pdp_handle* h, const double* J_next_host, double* 
             CUDA_TRY(h, cudaMemcpyAsync(pi_host + off, h->dpi + off, cnt * sizeof(long long), cudaMemcpyDeviceToHost, h->d2h_stream));
         }
     }
-    double cs[PDP_HOST_MAX_CHUNKS * 3];
-    CUDA_TRY(h, cudaMemcpyAsync(cs, h->dchunk_stats, (size_t)C * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    for (int i = 1; i < K; ++i) {   // join the side streams into the handle's stream
+        CUDA_TRY(h, cudaEventRecord(h->ev_side[i - 1], cs[i]));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_side[i - 1], 0));
+    }
+    double cst[PDP_HOST_MAX_CHUNKS * 3];
+    CUDA_TRY(h, cudaMemcpyAsync(cst, h->dchunk_stats, (size_t)C * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     h->cur_idx = 1 - h->cur_idx;
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->d2h_stream));
     if (stats_out) {
-        pdp_stats s = {cs[0], cs[1], cs[2]};
+        pdp_stats s = {cst[0], cst[1], cst[2]};
         for (int i = 1; i < C; ++i) {
-            s.j_max = std::max(s.j_max, cs[3 * i]);
-            s.delta_max = std::max(s.delta_max, cs[3 * i + 1]);
-            s.delta_min = std::min(s.delta_min, cs[3 * i + 2]);
+            s.j_max = std::max(s.j_max, cst[3 * i]);
+            s.delta_max = std::max(s.delta_max, cst[3 * i + 1]);
+            s.delta_min = std::min(s.delta_min, cst[3 * i + 2]);
         }
         *stats_out = s;
     }

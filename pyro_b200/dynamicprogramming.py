@@ -9,6 +9,7 @@ Mirrors pyro/planning/dynamicprogramming.py:
   get_lookup_table_controller()                                                :472
   save_latest(name) / load_J_next(name)                                        :481 / :489
   DynamicProgrammingWithLookUpTable                                            :505
+  PolicyEvaluator / PolicyEvaluatorWithLookUpTable                             :619 / :677
   LookUpTableController                                                        :27
 
 State visible after any sweep is the reference's: ``J`` (N,) float64, ``pi`` (N,) int64,
@@ -263,6 +264,55 @@ class DynamicProgrammingWithLookUpTable(DynamicProgramming):
     """Name kept for drop-in use: every reference example instantiates this class
     (dynamicprogramming.py:505).  Known systems run the fused on-the-fly kernel (no tables are
     ever materialised); anything else runs the LUT-mode kernel on the reference-style tables."""
+
+
+class PolicyEvaluator(DynamicProgramming):
+    """Evaluate the cost-to-go of a given control law (dynamicprogramming.py:619-672): the backup
+    J[s] = g(x_s, u_s)*dt + alpha*J_next(x_next_s) with u_s = ctl.c(x_s, ctl.rbar, t), INF where the
+    input or the arrival state is not allowed.  One column per node, no min: the tables of
+    PolicyEvaluatorWithLookUpTable (:683-729) are built once on the host exactly as the reference builds
+    them and the sweeps run on the device in LUT mode (J = G + alpha*RGI(J_next)(x_next_table), :743-752)."""
+
+    def __init__(self, ctl, grid_sys, cost_function, final_time=0, engine_factory=None):
+        self.ctl = ctl
+        DynamicProgramming.__init__(self, grid_sys, cost_function, final_time, engine_factory)
+
+    def _extract(self):
+        return _problem.extract(self.grid_sys, self.cf, self.alpha, self.interpol_method, lut_actions=1)
+
+    def _make_engine(self, P):
+        if self._engine_factory is not None:
+            return self._engine_factory(self, P)
+        eng = Engine(P)
+        self.compute_lookuptable()
+        eng.set_lut(self.x_next_table, self.G)
+        return eng
+
+    def compute_lookuptable(self):
+        """x_next_table (N, n) and G (N,) of the control law (dynamicprogramming.py:683-729)."""
+        gs, sys, cf = self.grid_sys, self.sys, self.cf
+        X = gs.state_from_node_id
+        self.x_next_table = np.zeros((gs.nodes_n, sys.n), dtype=float)
+        self.G = np.zeros(gs.nodes_n, dtype=float)
+        for s in range(gs.nodes_n):
+            x = X[s, :]
+            u = self.ctl.c(x, self.ctl.rbar, self.t)
+            x_next = sys.f(x, u, self.t) * gs.dt + x
+            self.x_next_table[s, :] = x_next
+            if sys.isavalidinput(x, u) and sys.isavalidstate(x_next):
+                self.G[s] = cf.g(x, u, self.t) * gs.dt
+            else:
+                self.G[s] = cf.INF
+
+    def get_lookup_table_controller(self):
+        raise NotImplementedError("a policy evaluation has no policy table; the controller is self.ctl")
+
+    def clean_infeasible_set(self, tol=1):
+        raise NotImplementedError("clean_infeasible_set rewrites the policy; a policy evaluation has none")
+
+
+class PolicyEvaluatorWithLookUpTable(PolicyEvaluator):
+    """Name kept for drop-in use (dynamicprogramming.py:677); the look-up tables are always used."""
 
 
 def build_lookup_tables(grid_sys, cf, t=0):

@@ -123,14 +123,17 @@ def system_tables(sys, sys_id, x_level):
     return [_f64(t) for t in tabs], par
 
 
-def extract(grid_sys, cf, alpha=1.0, interpol_method="linear", slab=None, alloc_planes=0, force_lut=False):
-    """Build the descriptor for ``pdp_create``.  ``slab`` = (begin, end) axis-0 planes of this rank."""
+def extract(grid_sys, cf, alpha=1.0, interpol_method="linear", slab=None, alloc_planes=0, force_lut=False,
+            lut_actions=None):
+    """Build the descriptor for ``pdp_create``.  ``slab`` = (begin, end) axis-0 planes of this rank.
+    ``lut_actions``: LUT-mode descriptor with that many table columns per node instead of the grid's
+    action count (policy evaluation sweeps have exactly one, dynamicprogramming.py:683-752)."""
     sys = grid_sys.sys
     n, m = int(sys.n), int(sys.m)
     if n not in (2, 3, 4) or m not in (1, 2):
         raise NotImplementedError("grid DP supports n in {2,3,4}, m in {1,2} (discretizer.py:243-245,304-306)")
     sys_id, cost_id = classify(grid_sys, cf, interpol_method)
-    if force_lut:
+    if force_lut or lut_actions is not None:
         sys_id, cost_id = _lib.PDP_SYS_LUT, 0
 
     P = Problem()
@@ -141,10 +144,14 @@ def extract(grid_sys, cf, alpha=1.0, interpol_method="linear", slab=None, alloc_
     udims = [int(d) for d in grid_sys.u_grid_dim]
     if len(dims) != n or len(udims) != m:
         raise ValueError("grid dimensions do not match the system dimensions")
+    u_src = grid_sys.u_level
+    if lut_actions is not None:
+        udims = [int(lut_actions)] + [1] * (m - 1)
+        u_src = [np.zeros(d) for d in udims]   # placeholders: the tables carry the inputs' effect
     begin, end = (0, dims[0]) if slab is None else slab
     c.slab_begin, c.slab_end, c.alloc_planes = int(begin), int(end), int(alloc_planes)
     x_level = [P.hold(f"x_level{i}", grid_sys.x_level[i]) for i in range(n)]
-    u_level = [P.hold(f"u_level{i}", grid_sys.u_level[i]) for i in range(m)]
+    u_level = [P.hold(f"u_level{i}", u_src[i]) for i in range(m)]
     for i in range(n):
         if x_level[i].size != dims[i]:
             raise ValueError("x_level size does not match x_grid_dim")

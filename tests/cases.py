@@ -34,6 +34,29 @@ CASES = {
 }
 
 
+class LinearFeedback:
+    """Static state feedback u = -K (y - ref), the controller interface PolicyEvaluator reads
+    (pyro/control/controller.py: ``rbar`` and ``c(y, r, t)``).  Unsaturated on purpose, so that some
+    nodes ask for a disallowed input and take the INF branch with an in-bounds arrival state."""
+
+    def __init__(self, K, ref):
+        self.K = np.array(K, float)
+        self.ref = np.array(ref, float)
+        self.rbar = np.zeros(1)
+
+    def c(self, y, r, t=0):
+        return -np.dot(self.K, np.asarray(y, float) - self.ref)
+
+
+# policy evaluation (dynamicprogramming.py:619-752): J of a fixed control law, one table column per node
+POLICY_CASES = {
+    "pe_pend_pd": dict(system="SinglePendulum", x_grid_dim=[41, 37], u_grid_dim=[3], xbar=[-3.14, 0.0], INF=300.0,
+                       ctl=dict(K=[[0.5, 0.3]], ref=[-3.14, 0.0]), snapshots=[1, 5, 40]),
+    "pe_cartpole_lin": dict(system="CartPole", x_grid_dim=[7, 9, 7, 9], u_grid_dim=[3], xbar=[0.0, PI, 0.0, 0.0], INF=1000.0,
+                            alpha=0.9, ctl=dict(K=[[0.3, -1.0, 0.3, -0.4]], ref=[0.0, PI, 0.0, 0.0]), snapshots=[1, 3, 10]),
+}
+
+
 def build_case(case, lookup=False):
     """Instantiate a case on the pyro_b200 mirrors -> (sys, grid_sys, cf)."""
     from pyro_b200 import costfunction, discretizer, systems

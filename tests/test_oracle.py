@@ -7,7 +7,7 @@ import pytest
 
 from oracle import c_oracle, np_oracle as npo, ref_loader
 from pyro_b200 import problem
-from tests.cases import CASES, build_case, oracle_objects
+from tests.cases import CASES, POLICY_CASES, LinearFeedback, build_case, oracle_objects
 from tests.conftest import load_golden
 
 
@@ -119,3 +119,33 @@ def test_live_reference_base_class_equals_oracle():
     grid, cost = oracle_objects(case)
     J, pi, _ = grid.run(cost, 3)
     assert np.array_equal(J, dp.J) and np.array_equal(pi, dp.pi)
+
+
+@pytest.mark.parametrize("name", list(POLICY_CASES))
+def test_policy_evaluation_oracle_and_mirror_tables_match_reference(name):
+    """Policy evaluation (dynamicprogramming.py:677-752): the NumPy restatement J = G + alpha*RGI(J_next)(x_next)
+    reproduces the reference's snapshots from the reference's tables, and the mirror's compute_lookuptable
+    (host loop, same calls) rebuilds those tables bit for bit."""
+    case, gold = POLICY_CASES[name], load_golden(name)
+    _, grid, cf = build_case(case)
+    J = gold["J0"].copy()
+    k = 0
+    for target in case["snapshots"]:
+        for _ in range(target - k):
+            J, pi = npo.lut_sweep(grid.x_level, case["x_grid_dim"], J, gold["x_next_table"][:, None, :], gold["G"][:, None],
+                                  case.get("alpha", 1.0), use_scipy=False)
+            assert (pi == 0).all()
+        k = target
+        assert np.array_equal(J, gold[f"J_{k}"])
+    from pyro_b200 import dynamicprogramming as dpm
+
+    class NoEngine:  # host-side table build only: no device in the CPU suite
+        def __init__(self, N):
+            self.N, self.problem = N, type("P", (), {"system_id": 0})()
+        def set_J(self, J): pass
+        def get_J(self): return np.zeros(self.N)
+        def close(self): pass
+    pe = dpm.PolicyEvaluatorWithLookUpTable(LinearFeedback(**case["ctl"]), grid, cf,
+                                            engine_factory=lambda dp, P: NoEngine(grid.nodes_n))
+    pe.compute_lookuptable()
+    assert np.array_equal(pe.x_next_table, gold["x_next_table"]) and np.array_equal(pe.G, gold["G"])

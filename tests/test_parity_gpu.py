@@ -11,7 +11,7 @@ import pytest
 from oracle import c_oracle, np_oracle as npo
 from pyro_b200 import _lib, dynamicprogramming, problem
 from pyro_b200.engine import Engine
-from tests.cases import CASES, build_case, oracle_objects
+from tests.cases import CASES, POLICY_CASES, LinearFeedback, build_case, oracle_objects
 from tests.conftest import load_golden
 
 pytestmark = pytest.mark.gpu
@@ -314,3 +314,20 @@ def test_host_array_sweep_is_the_same_backup(name, chunks, monkeypatch):
     with pytest.raises(ValueError):
         eng.sweep_host(J0[:-1])
     eng.close()
+
+
+@pytest.mark.parametrize("name", list(POLICY_CASES))
+def test_policy_evaluation_matches_reference_goldens(name):
+    """PolicyEvaluatorWithLookUpTable (dynamicprogramming.py:677-752) through the public mirror class: tables built on
+    the host as the reference builds them, sweeps in LUT mode with one column per node; bit-exact J."""
+    case, gold = POLICY_CASES[name], load_golden(name)
+    _, grid, cf = build_case(case)
+    pe = dynamicprogramming.PolicyEvaluatorWithLookUpTable(LinearFeedback(**case["ctl"]), grid, cf)
+    pe.alpha, pe.verbose = case.get("alpha", 1.0), False
+    assert np.array_equal(pe.J, gold["J0"])
+    k = 0
+    for target in case["snapshots"]:
+        pe.compute_steps(target - k)
+        k = target
+        assert np.array_equal(pe.J, gold[f"J_{k}"]) and (pe.pi == 0).all()
+    assert np.array_equal(pe.x_next_table, gold["x_next_table"]) and np.array_equal(pe.G, gold["G"])
