@@ -265,6 +265,7 @@ def main():
 
     _, grid, cf = build_case(case)
     n, A, N = grid.sys.n, grid.actions_n, grid.nodes_n
+    torch.cuda.set_stream(torch.cuda.Stream())   # a real stream, not the legacy default one: torch events and the engine share it
     stream = torch.cuda.current_stream()
     if world > 1:
         eng = ShardedEngine(grid, cf, 1.0)
@@ -286,7 +287,7 @@ def main():
     barrier()
 
     # ---- timed region: K sweeps, L2 flushed before each, device time by CUDA events ----------------
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if (rank == 0 and not os.environ.get("BENCH_NO_SAMPLER")) else None
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = kernel_eng.launch_count
     barrier()
@@ -301,10 +302,12 @@ def main():
     t_wall = time.perf_counter() - t_wall0
     step_ms = np.array([s.elapsed_time(e) for s, e in ev])
     total_ms = float(step_ms.sum())
+    per_rank_ms = [total_ms / args.steps]
     if world > 1:
-        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+        allt = [torch.zeros(1, device="cuda", dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(allt, torch.tensor([total_ms], device="cuda", dtype=torch.float64))
+        per_rank_ms = [float(x.item()) / args.steps for x in allt]
+        total_ms = max(per_rank_ms) * args.steps
     launches = kernel_eng.launch_count - launches0
     clocks = sampler.stop() if sampler else None
 
@@ -355,7 +358,7 @@ def main():
             dist.all_reduce(t)
             J_host.copy_(t.cpu())
         held = (kernel_eng.alloc_end - kernel_eng.alloc_begin) * kernel_eng.plane
-        n_e2e = max(3, min(args.steps, 10))
+        n_e2e = max(5, min(args.steps, 20))
 
         if world == 1:
             J_in = torch.empty(N, dtype=torch.float64).pin_memory()
@@ -372,12 +375,15 @@ def main():
                 eng.sweep(1)                # sweep (+ halo exchange and stats all-reduce for N>1)
                 kernel_eng.get_J(Js_np)     # D2H: J of the slab
                 kernel_eng.get_pi(pis_np)   # D2H: pi of the slab
-        for _ in range(2):
+        for _ in range(3):
             e2e_step()
         barrier()
+        e2e_steps_ms = []
         t0 = time.perf_counter()
         for _ in range(n_e2e):
-            e2e_step()
+            t1 = time.perf_counter()
+            e2e_step()               # blocking call: returns when J and pi are in the host buffers
+            e2e_steps_ms.append(1e3 * (time.perf_counter() - t1))
         barrier()
         dt = time.perf_counter() - t0
         h2d, d2h = 8.0 * held, 16.0 * slab_n
@@ -389,6 +395,7 @@ def main():
             dt, h2d, d2h = float(mx[0].item()), float(t[2].item()), float(t[3].item())
         e2e = {"value": evals_per_step * n_e2e / dt, "unit": "evals/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": n_e2e, "ms_per_step": 1e3 * dt / n_e2e,
+               "step_ms_min_median_max": [float(np.min(e2e_steps_ms)), float(np.median(e2e_steps_ms)), float(np.max(e2e_steps_ms))],
                "call": ("pdp_sweep_host (H2D J_next -> sweep -> D2H J, pi; chunk-pipelined), pinned host buffers" if world == 1 else
                         "pdp_set_J + pdp_sweep(1) + pdp_get_J + pdp_get_pi, pinned host buffers "
                         "(per rank: its planes up, its slab down; halo exchange inside)")}
@@ -414,11 +421,11 @@ def main():
             "config": {"workload": wl_name, "system": case["system"], "x_grid_dim": case["x_grid_dim"],
                        "u_grid_dim": case["u_grid_dim"], "dt": case["dt"], "alpha": 1.0, "nodes": N, "actions": A,
                        "evals_per_step": evals_per_step,
-                       "parallelism": (f"slab{world}/{eng.mode}" + ("+overlap" if eng.overlap else "")) if world > 1 else "single",
+                       "parallelism": (f"slab{world}/{eng.mode}/{eng.halo}" + ("+overlap" if eng.overlap else "")) if world > 1 else "single",
                        "l2": f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)", "J0": "h(x) then warm-up sweeps"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu, "cpu_baseline_native": cpu_nat,
-            "wall_s_timed_region": t_wall, "step_ms_min_max": [float(step_ms.min()), float(step_ms.max())],
+            "wall_s_timed_region": t_wall, "ms_per_step_by_rank": per_rank_ms, "step_ms_min_max": [float(step_ms.min()), float(step_ms.max())],
             "last_sweep_stats": {"j_max": float(last_stats[-1][0]), "delta_max": float(last_stats[-1][1]), "delta_min": float(last_stats[-1][2])},
             "J_Linf_error": "see tests/test_parity_gpu.py (bit-exact vs reference goldens)",
         }

@@ -184,6 +184,14 @@ int pdp_clean_infeasible_set(pdp_handle* h, double tol, int64_t default_action);
 int pdp_nccl_unique_id(void* id128);
 int pdp_comm_init(pdp_handle* h, int32_t rank, int32_t world, const void* id128, int32_t exchange_mode, int32_t overlap);
 int pdp_exchange_current(pdp_handle* h);
+/* Peer-memory halo exchange (upgrade of halo mode): every rank exports CUDA IPC handles of its two J buffers
+ * and of a flag word pair (pdp_peer_export, 200 bytes), the caller hands each rank the exports of ranks r-1
+ * and r+1 (NULL at the ends), and from then on a sweep stores the planes its neighbours read straight into
+ * the neighbours' buffers over NVLink from a device kernel, publishes a sequence number with a system-scope
+ * fence, and waits on the device for the neighbours' numbers before the next sweep: no NCCL call, no side
+ * stream, no host step per sweep.  The communicator stays attached for the statistics all-reduce. */
+int pdp_peer_export(pdp_handle* h, void* out200);
+int pdp_peer_attach(pdp_handle* h, const void* lower200, const void* upper200);
 /* Caller-driven exchange (any transport): */
 int pdp_sweep_async(pdp_handle* h);
 int pdp_sweep_planes_async(pdp_handle* h, int32_t plane_begin, int32_t plane_end, int32_t stat_set);

@@ -59,6 +59,8 @@ SIGNATURES = {
     "pdp_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "pdp_comm_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32]),
     "pdp_exchange_current": (C.c_int, [C.c_void_p]),
+    "pdp_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pdp_peer_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pdp_set_lut": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pdp_get_input_from_policy": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "pdp_clean_infeasible_set": (C.c_int, [C.c_void_p, C.c_double, C.c_int64]),

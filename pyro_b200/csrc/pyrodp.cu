@@ -172,6 +172,44 @@ __global__ void stats_unfold_kernel(double* __restrict__ st, int n) {
     if (i < n) st[3 * i + 2] = -st[3 * i + 2];
 }
 
+// ---- peer-memory halo exchange (one process per GPU, buffers opened through CUDA IPC) -----------------
+// After a rank's slab planes of the new J are written, the planes its neighbours read as their halo are
+// stored straight into the neighbours' own J buffers over NVLink (peer pointers), followed by a
+// system-scope fence and one sequence-number flag per neighbour.  Before its next sweep a rank waits
+// (on the device) until both neighbours' flags carry the previous exchange's number.  No NCCL call,
+// no side stream, no host involvement per sweep.
+__global__ void halo_push_kernel(const double* __restrict__ src_lo, double* __restrict__ dst_lo, long long n_lo,
+                                 const double* __restrict__ src_hi, double* __restrict__ dst_hi, long long n_hi,
+                                 unsigned int* ticket, unsigned int* peer_flag_lo, unsigned int* peer_flag_hi, unsigned int seq) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_lo; i += stride) dst_lo[i] = src_lo[i];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_hi; i += stride) dst_hi[i] = src_hi[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(ticket, 1u);
+        if (t == gridDim.x - 1) {   // every block's stores are fenced: publish
+            __threadfence_system();
+            if (peer_flag_lo) *(volatile unsigned int*)peer_flag_lo = seq;
+            if (peer_flag_hi) *(volatile unsigned int*)peer_flag_hi = seq;
+            __threadfence_system();
+            *ticket = 0u;
+        }
+    }
+}
+// flags[0] is written by the rank below, flags[1] by the rank above.  Bounded spin: a peer that never
+// arrives raises *err instead of hanging the device.
+__global__ void halo_wait_kernel(const unsigned int* flags, unsigned int want, int has_lo, int has_hi, unsigned int* err,
+                                 long long timeout_cycles) {
+    const volatile unsigned int* f = flags;
+    const long long t0 = clock64();
+    while ((has_lo && (int)(f[0] - want) < 0) || (has_hi && (int)(f[1] - want) < 0)) {
+        if (clock64() - t0 > timeout_cycles) { *err = 1u; break; }
+        __nanosleep(100);
+    }
+    __threadfence_system();
+}
+
 // =================================================================================================
 // Host side: handle + C ABI
 // =================================================================================================
@@ -222,6 +260,12 @@ struct pdp_handle {
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_boundary = nullptr, ev_comm = nullptr;
     long long exchanges = 0;
+    // peer-memory halo exchange (exchange_mode 3)
+    unsigned int* dflags = nullptr;       // [0] written by the rank below, [1] by the rank above, [2] push ticket, [3] wait error
+    double* peer_J[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [below/above][buffer index], opened through CUDA IPC
+    unsigned int* peer_flags[2] = {nullptr, nullptr};
+    int peer_alloc_begin[2] = {0, 0};
+    unsigned int peer_seq = 0;            // number of exchanges pushed so far
     // pdp_sweep_host: copy streams, per-chunk events and statistics
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     cudaStream_t side_stream[2] = {nullptr, nullptr};  // chunk kernels rotate over {stream, side_stream[0], side_stream[1]}
@@ -571,6 +615,11 @@ extern "C" int pdp_destroy(pdp_handle* h) {
     for (void* p : h->owned) cudaFree(p);
     cudaFree(h->dJ[0]); cudaFree(h->dJ[1]); cudaFree(h->dpi); cudaFree(h->dstats); cudaFree(h->dstats_sets);
     cudaFree(h->dslots); cudaFree(h->dcounter); cudaFree(h->d_xnext); cudaFree(h->d_G);
+    for (int side = 0; side < 2; ++side) {
+        for (int b = 0; b < 2; ++b) if (h->peer_J[side][b]) cudaIpcCloseMemHandle(h->peer_J[side][b]);
+        if (h->peer_flags[side]) cudaIpcCloseMemHandle(h->peer_flags[side]);
+    }
+    cudaFree(h->dflags);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
     if (h->ev_boundary) cudaEventDestroy(h->ev_boundary);
@@ -871,6 +920,21 @@ static int exchange(pdp_handle* h, int which, cudaStream_t st) {
     double* base = h->dJ[which];  // element 0 = plane alloc_begin
     auto at = [&](int plane) { return base + (long long)(plane - h->alloc_begin) * h->plane; };
     h->exchanges += 1;
+    if (h->exchange_mode == 3) {
+        // my lowest halo_hi planes are the upper halo of the rank below; my highest halo_lo planes the lower halo of the rank above
+        const bool lo = h->rank > 0, hi = h->rank < h->world - 1;
+        const long long n_lo = lo ? (long long)h->halo_hi * h->plane : 0, n_hi = hi ? (long long)h->halo_lo * h->plane : 0;
+        double* dst_lo = lo ? h->peer_J[0][which] + (long long)(h->slab_begin - h->peer_alloc_begin[0]) * h->plane : nullptr;
+        double* dst_hi = hi ? h->peer_J[1][which] + (long long)(h->slab_end - h->halo_lo - h->peer_alloc_begin[1]) * h->plane : nullptr;
+        h->peer_seq += 1;
+        const long long n = std::max(n_lo, n_hi);
+        const int blocks = (int)std::min<long long>(std::max<long long>((n + 1023) / 1024, 1), 592);
+        halo_push_kernel<<<blocks, 256, 0, st>>>(at(h->slab_begin), dst_lo, n_lo, at(h->slab_end - h->halo_lo), dst_hi, n_hi,
+                                                 h->dflags + 2, lo ? h->peer_flags[0] + 1 : nullptr, hi ? h->peer_flags[1] + 0 : nullptr,
+                                                 h->peer_seq);
+        CUDA_TRY(h, cudaGetLastError());
+        return PDP_OK;
+    }
     if (h->exchange_mode == 2) {
         const size_t cnt = (size_t)(h->alloc_planes_cap / h->world) * h->plane;
         NCCL_TRY(h, g_nccl.AllGather(base + (size_t)h->rank * cnt, base, cnt, PDP_NCCL_F64, h->comm, st));
@@ -896,10 +960,17 @@ static int sharded_sweep_enqueue(pdp_handle* h, double* dst) {
     const int b = h->slab_begin, e = h->slab_end, lo = h->halo_lo, hi = h->halo_hi;
     double* sets = h->dstats_sets;
     int rc;
-    if (h->exchange_mode == 1 && h->overlap && b + hi < e - lo) {
+    if (h->exchange_mode == 3) {
+        // the halo planes of J[cur] were stored by the neighbours in exchange number peer_seq: wait for them on the device
+        halo_wait_kernel<<<1, 1, 0, h->stream>>>(h->dflags, h->peer_seq, h->rank > 0, h->rank < h->world - 1, h->dflags + 3,
+                                                 20000000000LL /* ~10 s */);
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    if ((h->exchange_mode == 1 || h->exchange_mode == 3) && h->overlap && b + hi < e - lo) {
         // Boundary planes + their exchange on the high-priority side stream, interior planes on the
         // main stream: the two kernels share the SMs (no serialised tail), the boundary blocks are
-        // scheduled first, and the NCCL send/recv runs under the interior planes.
+        // scheduled first, and the exchange (NCCL send/recv, or the peer-store kernel) runs under the
+        // interior planes — the neighbours' flags are up long before their next sweep asks for them.
         CUDA_TRY(h, cudaEventRecord(h->ev_boundary, h->stream));            // previous sweep (and its exchange) done
         CUDA_TRY(h, cudaStreamWaitEvent(h->comm_stream, h->ev_boundary, 0));
         if ((rc = launch_planes(h, b, b + hi, 1, sets + 3, h->comm_stream)) != PDP_OK) return rc;
@@ -966,8 +1037,12 @@ extern "C" int pdp_sweep_collect(pdp_handle* h, pdp_stats* stats_out, int32_t ma
     const int m = std::min(n, (int)max_out);
     if (stats_out && m > 0)
         CUDA_TRY(h, cudaMemcpyAsync(stats_out, h->dstats, (size_t)m * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    unsigned int wait_err = 0;
+    if (h->exchange_mode == 3)
+        CUDA_TRY(h, cudaMemcpyAsync(&wait_err, h->dflags + 3, sizeof(wait_err), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->enqueued = 0;
+    if (wait_err) return fail(h, PDP_ECUDA, "peer halo exchange: a neighbouring rank did not deliver its planes within the time limit");
     return PDP_OK;
 }
 
@@ -1086,7 +1161,56 @@ extern "C" int pdp_exchange_current(pdp_handle* h) {
     CHECK_HANDLE(h);
     int rc = exchange(h, h->cur_idx, h->stream);
     if (rc != PDP_OK) return rc;
+    if (h->exchange_mode == 3 && h->world > 1) {
+        halo_wait_kernel<<<1, 1, 0, h->stream>>>(h->dflags, h->peer_seq, h->rank > 0, h->rank < h->world - 1, h->dflags + 3,
+                                                 20000000000LL);
+        CUDA_TRY(h, cudaGetLastError());
+    }
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return PDP_OK;
+}
+
+// ---- peer-memory halo exchange: export / attach -------------------------------------------------------
+// out200 = {cudaIpcMemHandle_t J buffer 0, J buffer 1, flags (3 x 64 bytes), int32 alloc_begin, int32 pad}
+extern "C" int pdp_peer_export(pdp_handle* h, void* out200) {
+    CHECK_HANDLE(h);
+    if (!out200) return fail(h, PDP_EINVAL, "pdp_peer_export: null pointer");
+    if (!h->dflags) {
+        CUDA_TRY(h, cudaMalloc(&h->dflags, 4 * sizeof(unsigned int)));
+        CUDA_TRY(h, cudaMemset(h->dflags, 0, 4 * sizeof(unsigned int)));
+    }
+    cudaIpcMemHandle_t hd[3];
+    CUDA_TRY(h, cudaIpcGetMemHandle(&hd[0], h->dJ[0]));
+    CUDA_TRY(h, cudaIpcGetMemHandle(&hd[1], h->dJ[1]));
+    CUDA_TRY(h, cudaIpcGetMemHandle(&hd[2], h->dflags));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    memcpy(out200, hd, sizeof(hd));
+    int32_t tail[2] = {h->alloc_begin, 0};
+    memcpy((char*)out200 + sizeof(hd), tail, sizeof(tail));
+    return PDP_OK;
+}
+
+// lower200 / upper200: what pdp_peer_export produced on rank-1 / rank+1 (NULL at the ends).  Needs the halo
+// layout (slab + halo buffers) and a communicator for the statistics all-reduce (pdp_comm_init, halo mode).
+extern "C" int pdp_peer_attach(pdp_handle* h, const void* lower200, const void* upper200) {
+    CHECK_HANDLE(h);
+    if (!h->comm || h->exchange_mode != 1) return fail(h, PDP_ESTATE, "pdp_peer_attach: call pdp_comm_init in halo mode first");
+    if (!h->dflags) return fail(h, PDP_ESTATE, "pdp_peer_attach: call pdp_peer_export first");
+    if ((h->rank > 0) != (lower200 != nullptr) || (h->rank < h->world - 1) != (upper200 != nullptr))
+        return fail(h, PDP_EINVAL, "pdp_peer_attach: neighbour handles do not match the rank's position");
+    const void* src[2] = {lower200, upper200};
+    for (int side = 0; side < 2; ++side) {
+        if (!src[side]) continue;
+        cudaIpcMemHandle_t hd[3];
+        int32_t tail[2];
+        memcpy(hd, src[side], sizeof(hd));
+        memcpy(tail, (const char*)src[side] + sizeof(hd), sizeof(tail));
+        CUDA_TRY(h, cudaIpcOpenMemHandle((void**)&h->peer_J[side][0], hd[0], cudaIpcMemLazyEnablePeerAccess));
+        CUDA_TRY(h, cudaIpcOpenMemHandle((void**)&h->peer_J[side][1], hd[1], cudaIpcMemLazyEnablePeerAccess));
+        CUDA_TRY(h, cudaIpcOpenMemHandle((void**)&h->peer_flags[side], hd[2], cudaIpcMemLazyEnablePeerAccess));
+        h->peer_alloc_begin[side] = tail[0];
+    }
+    h->exchange_mode = 3;
     return PDP_OK;
 }
 

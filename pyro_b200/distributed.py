@@ -70,7 +70,7 @@ class ShardedEngine:
     """Same interface as ``engine.Engine`` (sweep / get_J / get_pi / ...), sharded over ranks."""
 
     def __init__(self, grid_sys, cf, alpha=1.0, interpol_method="linear", engine_factory=None, group=None,
-                 mode=None, overlap=True, backend=None):
+                 mode=None, overlap=True, backend=None, halo=None):
         import torch
         from . import problem as _problem
         dist = _dist()
@@ -121,10 +121,25 @@ class ShardedEngine:
         # exchange through torch.distributed on views of the engine's buffers (any transport; used by
         # the gloo tests of the slab / halo logic with CPU stand-in engines).
         self.backend = backend or ("torch" if self.cpu else "native")
+        self.halo = None
         if self.backend == "native":
             ident = [self.eng.nccl_unique_id() if self.rank == 0 else None]
             dist.broadcast_object_list(ident, src=self._peer(0), group=group)
             self.eng.comm_init(self.rank, self.world, ident[0], self.mode, self.overlap)
+            # halo planes by grouped NCCL send/recv (default), or by peer-memory stores over NVLink from a device kernel
+            # (halo="peer" / PYRODP_HALO=peer).  Measured on 2 B200s at cfg 2 (profiles/r01_halo_ab.txt): NCCL 0.350 ms/step on
+            # both ranks, run after run; peer stores 0.342-0.344 on the rank that never waits but 0.344-0.377 on the other
+            # (the device-side wait sits at the head of the step on the main stream) — so NCCL stays the default.
+            import os
+            self.halo = halo or os.environ.get("PYRODP_HALO", "nccl")
+            if self.mode == "halo" and self.halo == "peer" and self.world > 1:
+                exports = [None] * self.world
+                dist.all_gather_object(exports, self.eng.peer_export(), group=group)
+                self.eng.peer_attach(exports[self.rank - 1] if self.rank > 0 else None,
+                                     exports[self.rank + 1] if self.rank < self.world - 1 else None)
+                dist.barrier(group=group)   # every rank has its neighbours' buffers mapped before the first push
+            else:
+                self.halo = "nccl" if self.mode == "halo" else "allgather"
         elif self.overlap:
             self.comm_stream = torch.cuda.Stream()
             self.ev_boundary = torch.cuda.Event()
@@ -289,4 +304,6 @@ class ShardedEngine:
         return self.eng.launch_count
 
     def close(self):
+        if self.halo == "peer":
+            self.dist.barrier(group=self.group)   # no rank frees buffers a neighbour has mapped and may still be storing into
         self.eng.close()

@@ -121,6 +121,17 @@ class Engine:
         buf = C.create_string_buffer(bytes(unique_id), 128)
         self._ck(self.lib.pdp_comm_init(self.h, int(rank), int(world), buf, {"halo": 1, "allgather": 2}[mode], int(bool(overlap))))
 
+    def peer_export(self):
+        buf = C.create_string_buffer(200)
+        self._ck(self.lib.pdp_peer_export(self.h, buf))
+        return buf.raw
+
+    def peer_attach(self, lower, upper):
+        """lower / upper: peer_export() of ranks r-1 / r+1 (None at the ends)."""
+        lo = C.create_string_buffer(bytes(lower), 200) if lower is not None else None
+        hi = C.create_string_buffer(bytes(upper), 200) if upper is not None else None
+        self._ck(self.lib.pdp_peer_attach(self.h, lo, hi))
+
     def exchange_current(self):
         self._ck(self.lib.pdp_exchange_current(self.h))
 

@@ -32,10 +32,11 @@ def main():
         case, gold = CASES[name], load_golden(name)
         _, grid, cf = build_case(case)
         k = case["snapshots"][1]
-        for mode, overlap, backend in (("halo", True, "native"), ("halo", False, "native"), ("allgather", False, "native"),
-                                       ("halo", True, "torch"), ("allgather", False, "torch")):
+        for mode, overlap, backend, halo in (("halo", True, "native", "peer"), ("halo", False, "native", "peer"), ("halo", True, "native", "nccl"),
+                                             ("halo", False, "native", "nccl"), ("allgather", False, "native", None),
+                                             ("halo", True, "torch", None), ("allgather", False, "torch", None)):
             try:
-                eng = distributed.ShardedEngine(grid, cf, case.get("alpha", 1.0), mode=mode, overlap=overlap, backend=backend)
+                eng = distributed.ShardedEngine(grid, cf, case.get("alpha", 1.0), mode=mode, overlap=overlap, backend=backend, halo=halo)
             except ValueError:
                 if rank == 0:
                     print(f"[multigpu] {name} {mode}: halo does not fit {world} ranks, skipped")
@@ -48,7 +49,7 @@ def main():
             ok = ok and stats[-1, 0] == J.max() and stats[-1, 1] == d.max() and stats[-1, 2] == d.min()
             held = eng.alloc_end - eng.alloc_begin
             if rank == 0:
-                print(f"[multigpu] {name} W={world} {eng.backend} mode={eng.mode} overlap={eng.overlap} k={k} planes held {held}/{eng.n0} "
+                print(f"[multigpu] {name} W={world} {eng.backend} mode={eng.mode} halo={getattr(eng, 'halo', '-')} overlap={eng.overlap} k={k} planes held {held}/{eng.n0} "
                       f"halo=({eng.halo_lo},{eng.halo_hi}): {'OK' if ok else 'MISMATCH'}", flush=True)
             failures += 0 if ok else 1
             eng.close()
@@ -61,8 +62,8 @@ def main():
     single.sweep(3)
     Jref, piref = single.get_J(), single.get_pi()
     single.close()
-    for overlap in (True, False):
-        eng = distributed.ShardedEngine(grid, cf, 1.0, overlap=overlap)
+    for overlap, halo in ((True, "peer"), (False, "peer"), (True, "nccl"), (False, "nccl")):
+        eng = distributed.ShardedEngine(grid, cf, 1.0, overlap=overlap, halo=halo)
         eng.set_J(J0)
         eng.sweep_nowait()            # the non-blocking form the benchmark uses
         eng.sweep_nowait()
@@ -70,7 +71,18 @@ def main():
         eng.sweep(1)
         ok = np.array_equal(eng.get_J(), Jref) and np.array_equal(eng.get_pi(), piref)
         if rank == 0:
-            print(f"[multigpu] cartpole 33x21x19x23 random J W={world} mode={eng.mode} overlap={eng.overlap}: {'OK' if ok else 'MISMATCH'}", flush=True)
+            print(f"[multigpu] cartpole 33x21x19x23 random J W={world} mode={eng.mode} halo={eng.halo} overlap={eng.overlap}: {'OK' if ok else 'MISMATCH'}", flush=True)
+        failures += 0 if ok else 1
+        # clean_infeasible_set rewrites slab nodes; the neighbours' halo copies must follow (exchange of the CURRENT J)
+        eng.clean_infeasible_set(1.0, 3)
+        eng.sweep(1)
+        Jc = eng.get_J()
+        ref = Engine(problem.extract(grid, cf, 1.0))
+        ref.set_J(J0); ref.sweep(3); ref.clean_infeasible_set(1.0, 3); ref.sweep(1)
+        ok = np.array_equal(Jc, ref.get_J())
+        ref.close()
+        if rank == 0:
+            print(f"[multigpu] ... clean_infeasible_set + sweep, halo={eng.halo}: {'OK' if ok else 'MISMATCH'}", flush=True)
         failures += 0 if ok else 1
         eng.close()
     t = torch.tensor([failures], device="cuda")

@@ -185,6 +185,33 @@ def test_full_size_config2_sampled_against_oracle_and_properties():
     eng.close()
 
 
+@pytest.mark.parametrize("name,case", [
+    ("cartpole_71", dict(system="CartPole", x_grid_dim=[71, 71, 71, 71], u_grid_dim=[51], xbar=[0.0, float(np.pi), 0.0, 0.0], INF=1000.0)),
+    ("twolink_51", dict(system="TwoLinkManipulator", x_grid_dim=[51, 51, 51, 51], u_grid_dim=[21, 21], INF=1000.0)),
+    ("dpend_51", dict(CASES["dpend_example"], x_grid_dim=[51, 51, 51, 51], u_grid_dim=[31, 31])),
+])
+def test_large_4d_grids_sampled_against_oracle(name, case):
+    """4-D grids of the BASELINE systems at sizes where G = 1 (one thread scans all actions of its node) and the
+    grid spans many blocks per (i0,i1) plane: random node ranges of one backup of a rough J against the C oracle."""
+    _, grid, cf = build_case(case)
+    P = problem.extract(grid, cf, 1.0)
+    eng = Engine(P)
+    assert eng.lanes_per_node == 1
+    rng = np.random.default_rng(2)
+    J0 = rng.uniform(0, 300, P.N)
+    eng.set_J(J0)
+    st = eng.sweep(1)
+    J1, pi1 = eng.get_J(), eng.get_pi()
+    plane = P.N // P.dims[0]
+    starts = list(rng.integers(0, P.N - 256, 20)) + [0, P.N - 256, plane * (P.dims[0] // 2) - 128]
+    for lo in starts:
+        Jr, pr = c_oracle.sweep_fused(P, J0, int(lo), int(lo) + 256)
+        assert np.array_equal(J1[lo:lo + 256], Jr) and np.array_equal(pi1[lo:lo + 256], pr), (name, int(lo))
+    d = J1 - J0
+    assert st[0, 0] == J1.max() and st[0, 1] == d.max() and st[0, 2] == d.min()
+    eng.close()
+
+
 def test_edge_cases():
     # smallest legal grid (2 levels per axis), a single action, and a grid where every transition leaves the box
     tiny = dict(system="SinglePendulum", x_grid_dim=[2, 2], u_grid_dim=[1], u_lb=[0.0], u_ub=[0.0], INF=9.0)
