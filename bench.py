@@ -72,55 +72,66 @@ def weak_scaled(case, world):
 
 
 class ClockSampler:
-    """SM clock / throttle reasons DURING the timed region (NVML polled from a thread every ~2 ms;
-    nvidia-smi's 100 ms loop is too coarse for a timed region of a few milliseconds)."""
+    """SM clock / throttle reasons DURING the timed region: NVML polled every ~2 ms (nvidia-smi's 100 ms loop is
+    too coarse for a timed region of a few milliseconds) — in a helper PROCESS, so that the benchmark process
+    itself never opens an NVML session or runs a polling thread beside its own CUDA calls."""
 
     def __init__(self, gpu_index):
-        import threading
-        self.samples, self.reasons, self.ok = [], set(), False
-        self._stop = threading.Event()
+        self.proc, self.ok = None, False
         try:
-            import pynvml as nv
-            nv.nvmlInit()
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            idx = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
-            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(idx)
-            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
-            self.ok = True
-        except Exception as exc:  # no NVML: report nulls, never fail the bench
-            self.err = repr(exc)
-            return
-        self.t = threading.Thread(target=self._run, daemon=True)
-        self.t.start()
-
-    def _run(self):
-        nv = self.nv
-        names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
-                 nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap",
-                 nv.nvmlClocksEventReasonHwPowerBrakeSlowdown: "hw_power_brake_slowdown"}
-        while not self._stop.is_set():
-            try:
-                self.samples.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)),
-                                     nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0))
-                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                for bit, name in names.items():
-                    if mask & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            time.sleep(0.002)
+            self.proc = subprocess.Popen([sys.executable, os.path.abspath(__file__), "--clock-sampler", str(gpu_index)],
+                                         stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.ok = self.proc.stdout.readline().strip() == "ready"
+        except Exception:
+            self.ok = False
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if not self.ok:
             return out
-        self._stop.set()
-        self.t.join(timeout=2)
-        if self.samples:
-            sm = [x[0] for x in self.samples]
-            out.update(sm_mhz=float(np.median(sm)), sm_min_mhz=float(min(sm)), sm_max_mhz=self.max_mhz,
-                       power_w_max=float(max(x[1] for x in self.samples)), reasons=sorted(self.reasons), samples=len(sm))
+        try:
+            self.proc.stdin.close()             # end of the timed region
+            line = self.proc.stdout.readline()
+            self.proc.wait(timeout=5)
+            out.update(json.loads(line))
+        except Exception:
+            pass
         return out
+
+
+def clock_sampler_main(gpu_index):
+    """Helper process: poll NVML until stdin closes, then print one JSON summary."""
+    import select
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
+        h = nv.nvmlDeviceGetHandleByIndex(idx)
+        max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+    except Exception:
+        print("unavailable", flush=True)
+        return
+    names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+             nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap",
+             nv.nvmlClocksEventReasonHwPowerBrakeSlowdown: "hw_power_brake_slowdown"}
+    samples, reasons = [], set()
+    print("ready", flush=True)
+    while True:
+        try:
+            samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), nv.nvmlDeviceGetPowerUsage(h) / 1000.0))
+            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            for bit, name in names.items():
+                if mask & bit:
+                    reasons.add(name)
+        except Exception:
+            pass
+        if select.select([sys.stdin], [], [], 0.002)[0]:   # EOF on stdin = stop
+            break
+    sm = [x[0] for x in samples] or [0.0]
+    print(json.dumps({"sm_mhz": float(np.median(sm)), "sm_min_mhz": float(min(sm)), "sm_max_mhz": max_mhz,
+                      "power_w_max": float(max(x[1] for x in samples)) if samples else None,
+                      "reasons": sorted(reasons), "samples": len(samples)}), flush=True)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -223,6 +234,8 @@ def run_reference_arm(args, case, wl_name):
 # own arm
 # --------------------------------------------------------------------------------------------------
 def main():
+    if len(sys.argv) >= 3 and sys.argv[1] == "--clock-sampler":
+        return clock_sampler_main(int(sys.argv[2]))
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -285,62 +298,13 @@ def main():
     for _ in range(args.warmup):
         eng.sweep(1)
     barrier()
-
-    # ---- timed region: K sweeps, L2 flushed before each, device time by CUDA events ----------------
-    sampler = ClockSampler(local_rank) if (rank == 0 and not os.environ.get("BENCH_NO_SAMPLER")) else None
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    launches0 = kernel_eng.launch_count
-    barrier()
-    t_wall0 = time.perf_counter()
-    for s, e in ev:
-        flush.zero_()            # write 256 MB > L2: the next sweep re-reads J_next from HBM
-        s.record()
-        eng.sweep_nowait()       # one Bellman sweep incl. the fused dJ statistics (+ halo exchange for N>1), enqueued
-        e.record()               # asynchronously: the host never waits inside the timed region
-    last_stats = eng.collect_stats()  # the K statistics triples (one small D2H; all-reduced over ranks for N>1)
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    step_ms = np.array([s.elapsed_time(e) for s, e in ev])
-    total_ms = float(step_ms.sum())
-    per_rank_ms = [total_ms / args.steps]
-    if world > 1:
-        allt = [torch.zeros(1, device="cuda", dtype=torch.float64) for _ in range(world)]
-        dist.all_gather(allt, torch.tensor([total_ms], device="cuda", dtype=torch.float64))
-        per_rank_ms = [float(x.item()) / args.steps for x in allt]
-        total_ms = max(per_rank_ms) * args.steps
-    launches = kernel_eng.launch_count - launches0
-    clocks = sampler.stop() if sampler else None
-
     evals_per_step = float(N) * A
-    value = evals_per_step * args.steps / (total_ms * 1e-3)
-
-    # ---- dominant kernel alone: back-to-back launches on the stream, events around the batch --------
-    kb = max(args.steps, 5)
-    if world == 1:
-        torch.cuda.synchronize()
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        flush.zero_()
-        k0.record()
-        eng.sweep(kb)
-        k1.record()
-        torch.cuda.synchronize()
-        kernel_ms = k0.elapsed_time(k1) / kb
-    else:
-        kernel_ms = total_ms / args.steps
-    peak, peak_src = measured_peak()
-    slab_evals = evals_per_step / world
-    achieved = slab_evals * b_eval(n, A) / (kernel_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
-                "kernel": {1: "sweep_pendulum_kernel", 2: "sweep_mech2_kernel<TWOLINK>", 3: "sweep_mech2_kernel<CARTPOLE>"}[kernel_eng.problem.system_id],
-                "kernel_ms": kernel_ms, "algorithmic_bytes_per_eval": b_eval(n, A),
-                "algorithmic_bytes_per_launch": slab_evals * b_eval(n, A),
-                "compulsory_dram_bytes_per_launch": 24.0 * N / world,
-                "note": "contract figure of SURVEY 8(d): the 2^n-corner J gather is served by L1/L2, so DRAM traffic is ~24 B/node "
-                        "and frac can exceed 1; the binding resource is the FP64 pipe (see DESIGN.md, profiles/)"}
 
     # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region ----
     e2e = None
+    # (measured before the clock sampler starts, so that no NVML polling runs beside the host<->device pipeline.
+    #  On these virtualised hosts the same call varies 0.52-0.68 ms from process to process, the first process on a
+    #  fresh box being the slow one: profiles/r01w_e2e_sampler.txt, profiles/r01o_e2e_chunks.jsonl)
     if not args.no_e2e:
         # every rank holds the full host J (the reference API's array) but uploads only the planes it
         # keeps (slab + halo) and reads back only its own slab of J and pi
@@ -399,6 +363,58 @@ def main():
                "call": ("pdp_sweep_host (H2D J_next -> sweep -> D2H J, pi; chunk-pipelined), pinned host buffers" if world == 1 else
                         "pdp_set_J + pdp_sweep(1) + pdp_get_J + pdp_get_pi, pinned host buffers "
                         "(per rank: its planes up, its slab down; halo exchange inside)")}
+
+    # ---- timed region: K sweeps, L2 flushed before each, device time by CUDA events ----------------
+    sampler = ClockSampler(local_rank) if (rank == 0 and not os.environ.get("BENCH_NO_SAMPLER")) else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = kernel_eng.launch_count
+    barrier()
+    t_wall0 = time.perf_counter()
+    for s, e in ev:
+        flush.zero_()            # write 256 MB > L2: the next sweep re-reads J_next from HBM
+        s.record()
+        eng.sweep_nowait()       # one Bellman sweep incl. the fused dJ statistics (+ halo exchange for N>1), enqueued
+        e.record()               # asynchronously: the host never waits inside the timed region
+    last_stats = eng.collect_stats()  # the K statistics triples (one small D2H; all-reduced over ranks for N>1)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    step_ms = np.array([s.elapsed_time(e) for s, e in ev])
+    total_ms = float(step_ms.sum())
+    per_rank_ms = [total_ms / args.steps]
+    if world > 1:
+        allt = [torch.zeros(1, device="cuda", dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(allt, torch.tensor([total_ms], device="cuda", dtype=torch.float64))
+        per_rank_ms = [float(x.item()) / args.steps for x in allt]
+        total_ms = max(per_rank_ms) * args.steps
+    launches = kernel_eng.launch_count - launches0
+    clocks = sampler.stop() if sampler else None
+
+    value = evals_per_step * args.steps / (total_ms * 1e-3)
+
+    # ---- dominant kernel alone: back-to-back launches on the stream, events around the batch --------
+    kb = max(args.steps, 5)
+    if world == 1:
+        torch.cuda.synchronize()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flush.zero_()
+        k0.record()
+        eng.sweep(kb)
+        k1.record()
+        torch.cuda.synchronize()
+        kernel_ms = k0.elapsed_time(k1) / kb
+    else:
+        kernel_ms = total_ms / args.steps
+    peak, peak_src = measured_peak()
+    slab_evals = evals_per_step / world
+    achieved = slab_evals * b_eval(n, A) / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
+                "kernel": {1: "sweep_pendulum_kernel", 2: "sweep_mech2_kernel<TWOLINK>", 3: "sweep_mech2_kernel<CARTPOLE>"}[kernel_eng.problem.system_id],
+                "kernel_ms": kernel_ms, "algorithmic_bytes_per_eval": b_eval(n, A),
+                "algorithmic_bytes_per_launch": slab_evals * b_eval(n, A),
+                "compulsory_dram_bytes_per_launch": 24.0 * N / world,
+                "note": "contract figure of SURVEY 8(d): the 2^n-corner J gather is served by L1/L2, so DRAM traffic is ~24 B/node "
+                        "and frac can exceed 1; the binding resource is the FP64 pipe (see DESIGN.md, profiles/)"}
 
     # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------------------------------
     cpu = cpu_nat = None

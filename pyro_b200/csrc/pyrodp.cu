@@ -272,7 +272,11 @@ struct pdp_handle {
     cudaEvent_t ev_side[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> ev_up, ev_done;
     cudaEvent_t ev_start = nullptr;
+    cudaEvent_t ev_join[2] = {nullptr, nullptr};
     double* dchunk_stats = nullptr;
+    double* h_chunk_stats = nullptr;     // pinned host copy of the per-chunk statistics
+    struct HostGraph { const void* jin; void* jout; void* piout; int cur_idx; int chunks; cudaGraphExec_t exec; };
+    std::vector<HostGraph> host_graphs;  // captured pdp_sweep_host pipelines, keyed by buffers, J parity and chunking
 
     long long slab_nodes() const { return (long long)(slab_end - slab_begin) * plane; }
     long long alloc_nodes() const { return (long long)(alloc_end - alloc_begin) * plane; }
@@ -634,6 +638,9 @@ extern "C" int pdp_destroy(pdp_handle* h) {
     if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
     if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     cudaFree(h->dchunk_stats);
+    if (h->h_chunk_stats) cudaFreeHost(h->h_chunk_stats);
+    for (auto& g : h->host_graphs) cudaGraphExecDestroy(g.exec);
+    for (int i = 0; i < 2; ++i) if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -1072,31 +1079,11 @@ extern "C" int pdp_sweep(pdp_handle* h, int32_t n_sweeps, pdp_stats* stats_out) 
 // buffers the PCIe transfers in both directions overlap the kernels; pageable buffers work but
 // serialise.  Afterwards the handle's state is as after pdp_set_J(J_next) + pdp_sweep(1).
 #define PDP_HOST_MAX_CHUNKS 64
-extern "C" int pdp_sweep_host(pdp_handle* h, const double* J_next_host, double* J_host, int64_t* pi_host, pdp_stats* stats_out) {
-    CHECK_HANDLE(h);
-    if (!J_next_host || !J_host || !pi_host) return fail(h, PDP_EINVAL, "pdp_sweep_host: null pointer");
-    if (h->comm || h->slab_nodes() != h->N) return fail(h, PDP_ESTATE, "pdp_sweep_host: the handle must own the whole grid (single GPU)");
-    if (h->enqueued || h->pending) return fail(h, PDP_ESTATE, "pdp_sweep_host: collect / commit the outstanding sweeps first");
-    int C = 8;
-    if (const char* env = getenv("PYRODP_HOST_CHUNKS")) C = atoi(env);
-    C = std::max(1, std::min(std::min(C, PDP_HOST_MAX_CHUNKS), h->n0));
-    if (!h->h2d_stream) {
-        CUDA_TRY(h, cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
-        CUDA_TRY(h, cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
-        CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
-        CUDA_TRY(h, cudaMalloc(&h->dchunk_stats, PDP_HOST_MAX_CHUNKS * 3 * sizeof(double)));
-        for (int i = 0; i < 2; ++i) {
-            CUDA_TRY(h, cudaStreamCreateWithFlags(&h->side_stream[i], cudaStreamNonBlocking));
-            CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_side[i], cudaEventDisableTiming));
-        }
-    }
-    while ((int)h->ev_up.size() < C) {
-        cudaEvent_t a = nullptr, b = nullptr;
-        CUDA_TRY(h, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
-        h->ev_up.push_back(a);
-        CUDA_TRY(h, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
-        h->ev_done.push_back(b);
-    }
+
+// Enqueue the whole pipeline of one host-array sweep; every stream it uses has rejoined h->stream when it
+// returns, and the per-chunk statistics land in the handle's pinned host buffer.  Runs either directly or
+// under stream capture (then nothing executes and the work becomes a CUDA graph).
+static int host_pipeline_enqueue(pdp_handle* h, const double* J_next_host, double* J_host, int64_t* pi_host, int C) {
     std::vector<int> bound(C + 1);
     for (int i = 0; i <= C; ++i) bound[i] = (int)((long long)i * h->n0 / C);
     double* Jc = h->dJ[h->cur_idx];
@@ -1116,7 +1103,6 @@ extern "C" int pdp_sweep_host(pdp_handle* h, const double* J_next_host, double* 
         if (cnt) CUDA_TRY(h, cudaMemcpyAsync(Jc + off, J_next_host + off, cnt * sizeof(double), cudaMemcpyHostToDevice, h->h2d_stream));
         CUDA_TRY(h, cudaEventRecord(h->ev_up[i], h->h2d_stream));
     }
-    h->have_J = true;
     int waited[3] = {-1, -1, -1};  // uploads [0..waited] are already ordered before that compute stream
     for (int i = 0; i < C; ++i) {
         // the chunk's backups read planes < bound[i+1] + halo_hi (and > bound[i] - halo_lo: uploaded earlier)
@@ -1135,16 +1121,107 @@ extern "C" int pdp_sweep_host(pdp_handle* h, const double* J_next_host, double* 
             CUDA_TRY(h, cudaMemcpyAsync(pi_host + off, h->dpi + off, cnt * sizeof(long long), cudaMemcpyDeviceToHost, h->d2h_stream));
         }
     }
-    for (int i = 1; i < K; ++i) {   // join the side streams into the handle's stream
+    // join: side compute streams, the upload stream (it has no successor otherwise) and the download stream
+    for (int i = 1; i < K; ++i) {
         CUDA_TRY(h, cudaEventRecord(h->ev_side[i - 1], cs[i]));
         CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_side[i - 1], 0));
     }
-    double cst[PDP_HOST_MAX_CHUNKS * 3];
-    CUDA_TRY(h, cudaMemcpyAsync(cst, h->dchunk_stats, (size_t)C * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_chunk_stats, h->dchunk_stats, (size_t)C * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaEventRecord(h->ev_join[0], h->h2d_stream));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_join[0], 0));
+    CUDA_TRY(h, cudaEventRecord(h->ev_join[1], h->d2h_stream));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_join[1], 0));
+    return PDP_OK;
+}
+
+static bool is_pinned_host(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+extern "C" int pdp_sweep_host(pdp_handle* h, const double* J_next_host, double* J_host, int64_t* pi_host, pdp_stats* stats_out) {
+    CHECK_HANDLE(h);
+    if (!J_next_host || !J_host || !pi_host) return fail(h, PDP_EINVAL, "pdp_sweep_host: null pointer");
+    if (h->comm || h->slab_nodes() != h->N) return fail(h, PDP_ESTATE, "pdp_sweep_host: the handle must own the whole grid (single GPU)");
+    if (h->enqueued || h->pending) return fail(h, PDP_ESTATE, "pdp_sweep_host: collect / commit the outstanding sweeps first");
+    if (h->P.system_id == PDP_SYS_LUT && !h->have_lut) return fail(h, PDP_ESTATE, "pdp_sweep: LUT mode needs pdp_set_lut first");
+    int C = 8;
+    if (const char* env = getenv("PYRODP_HOST_CHUNKS")) C = atoi(env);
+    C = std::max(1, std::min(std::min(C, PDP_HOST_MAX_CHUNKS), h->n0));
+    if (!h->h2d_stream) {
+        CUDA_TRY(h, cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
+        CUDA_TRY(h, cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
+        CUDA_TRY(h, cudaMalloc(&h->dchunk_stats, PDP_HOST_MAX_CHUNKS * 3 * sizeof(double)));
+        CUDA_TRY(h, cudaMallocHost(&h->h_chunk_stats, PDP_HOST_MAX_CHUNKS * 3 * sizeof(double)));
+        for (int i = 0; i < 2; ++i) {
+            CUDA_TRY(h, cudaStreamCreateWithFlags(&h->side_stream[i], cudaStreamNonBlocking));
+            CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_side[i], cudaEventDisableTiming));
+            CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
+        }
+    }
+    while ((int)h->ev_up.size() < C) {
+        cudaEvent_t a = nullptr, b = nullptr;
+        CUDA_TRY(h, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        h->ev_up.push_back(a);
+        CUDA_TRY(h, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        h->ev_done.push_back(b);
+    }
+    // With pinned host buffers the pipeline (≈ 8 x {2 copies, 1 kernel, 4 event operations} + joins) is captured
+    // once per {buffers, J parity} into a CUDA graph and replayed with ONE launch per call: the host cost of a
+    // step no longer depends on the chunk count.  Pageable buffers (or PYRODP_HOST_GRAPH=0) enqueue directly.
+    bool use_graph = is_pinned_host(J_next_host) && is_pinned_host(J_host) && is_pinned_host(pi_host);
+    if (const char* env = getenv("PYRODP_HOST_GRAPH")) use_graph = use_graph && atoi(env) != 0;
+    h->have_J = true;
+    if (use_graph) {
+        pdp_handle::HostGraph* g = nullptr;
+        for (auto& c : h->host_graphs)
+            if (c.jin == J_next_host && c.jout == J_host && c.piout == pi_host && c.cur_idx == h->cur_idx && c.chunks == C) g = &c;
+        if (!g) {
+            const long long launches0 = h->launches;
+            cudaGraph_t graph = nullptr;
+            int rc = PDP_OK;
+            // (the legacy default stream cannot be captured: then the direct path runs)
+            cudaError_t ce = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+            if (ce == cudaSuccess) {
+                rc = host_pipeline_enqueue(h, J_next_host, J_host, pi_host, C);
+                ce = cudaStreamEndCapture(h->stream, &graph);
+            }
+            h->launches = launches0;
+            if (rc != PDP_OK || ce != cudaSuccess || !graph) {
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+                h->sticky = 0;              // a failed capture leaves the device healthy: fall back to the direct path
+                use_graph = false;
+            } else {
+                cudaGraphExec_t exec = nullptr;
+                ce = cudaGraphInstantiate(&exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ce != cudaSuccess) { cudaGetLastError(); use_graph = false; }
+                else {
+                    if (h->host_graphs.size() >= 8) {   // bounded cache: drop the oldest
+                        cudaGraphExecDestroy(h->host_graphs.front().exec);
+                        h->host_graphs.erase(h->host_graphs.begin());
+                    }
+                    h->host_graphs.push_back({J_next_host, J_host, pi_host, h->cur_idx, C, exec});
+                    g = &h->host_graphs.back();
+                }
+            }
+        }
+        if (use_graph) {
+            CUDA_TRY(h, cudaGraphLaunch(g->exec, h->stream));
+            h->launches += C;
+        }
+    }
+    if (!use_graph) {
+        int rc = host_pipeline_enqueue(h, J_next_host, J_host, pi_host, C);
+        if (rc != PDP_OK) return rc;
+    }
     h->cur_idx = 1 - h->cur_idx;
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->d2h_stream));
     if (stats_out) {
+        const double* cst = h->h_chunk_stats;
         pdp_stats s = {cst[0], cst[1], cst[2]};
         for (int i = 1; i < C; ++i) {
             s.j_max = std::max(s.j_max, cst[3 * i]);

@@ -316,12 +316,23 @@ def test_every_lane_split_matches_goldens(name, lanes, generic, monkeypatch):
     eng.close()
 
 
+@pytest.mark.parametrize("pinned", [False, True])
 @pytest.mark.parametrize("chunks", [1, 3, 8, 64])
 @pytest.mark.parametrize("name", ["pend_301", "cartpole_25", "dpend_21"])
-def test_host_array_sweep_is_the_same_backup(name, chunks, monkeypatch):
+def test_host_array_sweep_is_the_same_backup(name, chunks, pinned, monkeypatch):
     """pdp_sweep_host (host arrays in/out, chunk-pipelined copies) == pdp_set_J + pdp_sweep + getters, for any
-    chunking (a chunk's backups read its halo planes, which must have been uploaded before it runs)."""
+    chunking (a chunk's backups read its halo planes, which must have been uploaded before it runs); with
+    pinned buffers the pipeline is captured into a CUDA graph and replayed, with pageable ones enqueued directly."""
     monkeypatch.setenv("PYRODP_HOST_CHUNKS", str(chunks))
+    if pinned:
+        import torch
+
+        def host(a):
+            t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+            return t.numpy()
+    else:
+        def host(a):
+            return a
     case = MID[name]
     _, grid, cf = build_case(case)
     P = problem.extract(grid, cf, case.get("alpha", 1.0))
@@ -331,10 +342,13 @@ def test_host_array_sweep_is_the_same_backup(name, chunks, monkeypatch):
     st_ref = eng.sweep(1)
     J_ref, pi_ref = eng.get_J(), eng.get_pi()
     eng.set_J(np.zeros(P.N))              # make sure the result really comes from the uploaded array
-    J, pi, st = eng.sweep_host(J0)
-    assert np.array_equal(J, J_ref) and np.array_equal(pi, pi_ref) and np.array_equal(st, st_ref[0])
+    Jin, Jout, piout = host(J0.copy()), host(np.empty(P.N)), host(np.empty(P.N, dtype=np.int64))
+    for rep in range(3 if pinned else 1):  # replays of the captured graph (both J parities) give the same answer
+        Jout[:] = -1.0
+        J, pi, st = eng.sweep_host(Jin, Jout, piout)
+        assert np.array_equal(J, J_ref) and np.array_equal(pi, pi_ref) and np.array_equal(st, st_ref[0])
     assert np.array_equal(eng.get_J(), J_ref) and np.array_equal(eng.get_J_next(), J0) and np.array_equal(eng.get_pi(), pi_ref)
-    J2, pi2, _ = eng.sweep_host(J)        # chained: second backup equals sweeping on
+    J2, pi2, _ = eng.sweep_host(host(J.copy()))   # chained: second backup equals sweeping on
     eng.set_J(J0)
     eng.sweep(2)
     assert np.array_equal(J2, eng.get_J()) and np.array_equal(pi2, eng.get_pi())
