@@ -62,6 +62,25 @@ def ncu_traffic(workload):
     return None
 
 
+def issue_model(system_id, evals, kernel_ms, clocks):
+    """What actually bounds the sweep: an FP64 warp instruction holds a sub-partition's issue
+    port for two cycles (scripts/micro/fp64_peak.cu, profiles/r01_fp64_peak_micro.txt), so a warp costs
+    2*FP64 + other instructions.  Instruction counts per warp-eval are ncu's (profiles/r01l / r01x source page);
+    the measured cycles come from this run's kernel time."""
+    if system_id != 1:
+        return {"resource": "issue port + L1 data pipe (see DESIGN.md section 5, profiles/r01b_cp101.txt)"}
+    import torch
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    measured = kernel_ms * 1e-3 * mhz * 1e6 * sms * 4 / (evals / 32.0)
+    f64, other = 19.45, 21.15
+    return {"resource": "issue port: FP64 warp instructions take 2 issue cycles", "fp64_inst_per_warp_eval": f64,
+            "other_inst_per_warp_eval": other, "model_cycles_per_warp_eval": 2 * f64 + other,
+            "measured_cycles_per_warp_eval": measured, "frac_of_issue_limit": (2 * f64 + other) / measured,
+            "arithmetic_floor_cycles_per_warp_eval": 2 * 17.5 + 3.0,
+            "source": "profiles/r01l (ncu source page counts), profiles/r01_fp64_peak_micro.txt"}
+
+
 def weak_scaled(case, world):
     """Per-GPU work fixed: axis 0 carries world x the planes of the named configuration."""
     case = dict(case)
@@ -324,21 +343,11 @@ def main():
         held = (kernel_eng.alloc_end - kernel_eng.alloc_begin) * kernel_eng.plane
         n_e2e = max(5, min(args.steps, 20))
 
-        if world == 1:
-            J_in = torch.empty(N, dtype=torch.float64).pin_memory()
-            J_in.copy_(torch.from_numpy(Js_np))   # the current J: every timed step repeats the same backup
-            Jin_np = J_in.numpy()
-
-            def e2e_step():
-                # ONE C-ABI call with host arrays on both sides (pdp_sweep_host): H2D of J_next, the sweep,
-                # D2H of J and pi, pipelined over plane chunks on three streams
-                kernel_eng.sweep_host(Jin_np, Js_np, pis_np)
-        else:
-            def e2e_step():
-                eng.set_J(J_np)             # H2D: J_next planes this rank holds
-                eng.sweep(1)                # sweep (+ halo exchange and stats all-reduce for N>1)
-                kernel_eng.get_J(Js_np)     # D2H: J of the slab
-                kernel_eng.get_pi(pis_np)   # D2H: pi of the slab
+        # ONE C-ABI call per step with host arrays on both sides (pdp_sweep_host): H2D of the J_next planes the rank
+        # holds (slab + halo of the full host array), the sweep, D2H of the slab's J and pi — pipelined over plane
+        # chunks and replayed as one CUDA graph.  A rank needs no halo exchange for a single host-to-host sweep.
+        def e2e_step():
+            kernel_eng.sweep_host(J_np, Js_np, pis_np)
         for _ in range(3):
             e2e_step()
         barrier()
@@ -357,12 +366,13 @@ def main():
             dist.all_reduce(mx, op=dist.ReduceOp.MAX)
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
             dt, h2d, d2h = float(mx[0].item()), float(t[2].item()), float(t[3].item())
+        if world > 1:
+            eng.set_J(J_np)   # device-resident sweeps continue from a J whose halo planes are current
         e2e = {"value": evals_per_step * n_e2e / dt, "unit": "evals/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": n_e2e, "ms_per_step": 1e3 * dt / n_e2e,
                "step_ms_min_median_max": [float(np.min(e2e_steps_ms)), float(np.median(e2e_steps_ms)), float(np.max(e2e_steps_ms))],
-               "call": ("pdp_sweep_host (H2D J_next -> sweep -> D2H J, pi; chunk-pipelined), pinned host buffers" if world == 1 else
-                        "pdp_set_J + pdp_sweep(1) + pdp_get_J + pdp_get_pi, pinned host buffers "
-                        "(per rank: its planes up, its slab down; halo exchange inside)")}
+               "call": "pdp_sweep_host (H2D J_next -> sweep -> D2H J, pi; chunk-pipelined, one CUDA graph), pinned host buffers"
+                       + (" (per rank: the planes it holds up, its slab down)" if world > 1 else "")}
 
     # ---- timed region: K sweeps, L2 flushed before each, device time by CUDA events ----------------
     sampler = ClockSampler(local_rank) if (rank == 0 and not os.environ.get("BENCH_NO_SAMPLER")) else None
@@ -413,6 +423,7 @@ def main():
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_eval": b_eval(n, A),
                 "algorithmic_bytes_per_launch": slab_evals * b_eval(n, A),
                 "compulsory_dram_bytes_per_launch": 24.0 * N / world,
+                "binding_resource": issue_model(kernel_eng.problem.system_id, slab_evals, kernel_ms, clocks),
                 "note": "contract figure of SURVEY 8(d): the 2^n-corner J gather is served by L1/L2, so DRAM traffic is ~24 B/node "
                         "and frac can exceed 1; the binding resource is the FP64 pipe (see DESIGN.md, profiles/)"}
 

@@ -152,8 +152,11 @@ int pdp_sweep_collect(pdp_handle* h, pdp_stats* stats_out, int32_t max_out, int3
 /* One sweep with HOST arrays on both sides — the reference's own calling convention, where J_next goes
  * in as a NumPy array and J, pi come out as NumPy arrays (dynamicprogramming.py:181-236): upload of
  * J_next (N doubles), backup, download of J (N doubles) and pi (N int64), pipelined over chunks of
- * axis-0 planes on three streams so that with pinned host buffers both PCIe directions overlap the
- * kernels.  Single-GPU handles only.  Afterwards the handle is as after pdp_set_J + pdp_sweep(1). */
+ * axis-0 planes so that with pinned host buffers both PCIe directions overlap the kernels (and the whole
+ * pipeline replays as one CUDA graph).  As with pdp_set_J / the getters, J_next_host is the FULL (N,) array
+ * and J_host / pi_host receive the handle's slab; a slab handle uploads the planes it holds (slab + halo),
+ * needs no exchange for this one sweep, and must refresh its halo (pdp_exchange_current or pdp_set_J) before
+ * device-resident sweeps continue.  On a single GPU the handle is afterwards as after pdp_set_J + pdp_sweep(1). */
 int pdp_sweep_host(pdp_handle* h, const double* J_next_host, double* J_host, int64_t* pi_host, pdp_stats* stats_out);
 
 /* LUT mode (system_id == PDP_SYS_LUT): the generic, bit-exact path for arbitrary user systems.

@@ -41,9 +41,15 @@ __device__ __forceinline__ double rgi_linear(const DevProblem& P, const double* 
     if (oob) return 0.0;  // fill_value (_rgi.py:476-477)
 #pragma unroll
     for (int d = 0; d < N; ++d) {
-        c[d] = find_cell(P.level[d], P.dims[d], x[d], P.lb[d], P.inv_step[d]);
-        const double lo = __ldg(P.level[d] + c[d]), hi = __ldg(P.level[d] + c[d] + 1);
-        y[d] = (x[d] - lo) / (hi - lo);
+        // scipy's find_interval_ascending: arithmetic guess, then the level table decides
+        const double* __restrict__ lev = P.level[d];
+        const int nlev = P.dims[d];
+        int k = min(max((int)((x[d] - P.lb[d]) * P.inv_step[d]), 0), nlev - 2);
+        double lo = __ldg(lev + k), hi = __ldg(lev + k + 1);
+        while (x[d] < lo && k > 0) { --k; hi = lo; lo = __ldg(lev + k); }
+        while (x[d] >= hi && k < nlev - 2) { ++k; lo = hi; hi = __ldg(lev + k + 1); }
+        c[d] = k;
+        y[d] = exact_div(x[d] - lo, hi - lo, __ldg(P.rinv[d] + k));   // correctly rounded quotient, 3 FP64 issues
     }
     if (N == 2) {
         const double* p = Jn + (long long)c[0] * P.dims[1] + c[1];
@@ -78,33 +84,108 @@ __global__ void __launch_bounds__(SWEEP_THREADS)
 sweep_lut_kernel(const __grid_constant__ DevProblem P, const double* __restrict__ Jn, double* __restrict__ Jo,
                  long long* __restrict__ pi, const double* __restrict__ xnext, const double* __restrict__ Gtab,
                  unsigned long long* __restrict__ partials, unsigned int* counter, double* __restrict__ stats) {
+    // Persistent grid: one resident wave of blocks strides over the nodes, so the statistics epilogue (three
+    // atomics and one ticket per BLOCK) stays negligible however many nodes there are — with one block per 128
+    // nodes the ticket counter alone serialised a 16M-node policy-evaluation sweep (r01B).
     const int lane_in_group = threadIdx.x % G;
-    const long long node = P.node_begin + ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
-    const long long slot = node - P.slab_node_begin;  // row of the (slab-local) x_next / G tables
     const int A = P.A;
+    const long long total = P.node_end - P.node_begin;
+    const long long gstride = (long long)gridDim.x * blockDim.x / G;
+    const long long iters = (total + gstride - 1) / gstride;   // the same trip count for every thread: shuffles inside
     Stats3 st = stats_identity();
-    const bool active = node < P.node_end;
-    double best = __longlong_as_double(0x7ff0000000000000LL);
-    int besta = 0x7fffffff;
-    if (active) {
-        const double* __restrict__ xrow = xnext + slot * (long long)A * N;
-        const double* __restrict__ grow = Gtab + slot * (long long)A;
-        for (int a = lane_in_group; a < A; a += G) {
-            double x[N];
+    for (long long it = 0; it < iters; ++it) {
+        const long long node = P.node_begin + it * gstride + ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+        const long long slot = node - P.slab_node_begin;  // row of the (slab-local) x_next / G tables
+        const bool active = node < P.node_end;
+        double best = __longlong_as_double(0x7ff0000000000000LL);
+        int besta = 0x7fffffff;
+        if (active) {
+            const double* __restrict__ xrow = xnext + slot * (long long)A * N;
+            const double* __restrict__ grow = Gtab + slot * (long long)A;
+            for (int a = lane_in_group; a < A; a += G) {
+                double x[N];
 #pragma unroll
-            for (int d = 0; d < N; ++d) x[d] = __ldcs(xrow + (long long)a * N + d);
-            bool oob;
-            const double Jx = rgi_linear<N>(P, Jn, x, oob);
-            const double Qa = __ldcs(grow + a) + P.alpha * Jx;
-            if (Qa < best) { best = Qa; besta = a; }
+                for (int d = 0; d < N; ++d) x[d] = __ldcs(xrow + (long long)a * N + d);
+                bool oob;
+                const double Jx = rgi_linear<N>(P, Jn, x, oob);
+                const double Qa = __ldcs(grow + a) + P.alpha * Jx;
+                if (Qa < best) { best = Qa; besta = a; }
+            }
+        }
+        lane_group_argmin(best, besta, G);
+        if (active && lane_in_group == 0) {
+            if (besta == 0x7fffffff) besta = 0;  // no Q below +inf: np.argmin of a constant row is 0
+            Jo[node] = best;
+            pi[node] = besta;
+            const double d = best - Jn[node];
+            Stats3 mine;
+            mine.jmax = best; mine.dmax = d; mine.dmin = d;
+            stats_merge(st, mine);
         }
     }
-    lane_group_argmin(best, besta, G);
-    if (active && lane_in_group == 0) {
-        Jo[node] = best;
-        pi[node] = besta;
-        const double d = best - Jn[node];
-        st.jmax = best; st.dmax = d; st.dmin = d;
+    block_stats_finish(st, partials, counter, stats);
+}
+
+// ---- policy evaluation: LUT mode with ONE table column per node (dynamicprogramming.py:743-752) --------
+// J = G + alpha * RGI(J_next)(x_next_table): no min, 8n + 32 bytes of HBM traffic per node and a few dozen
+// instructions — the streaming member of the family.  A persistent grid strides over the nodes; each thread
+// takes U nodes per trip (a grid-strided tile, so every access of a warp is contiguous) and issues all their
+// table loads before the first interpolation.  Measured (r01E, 4001^2 nodes): U = 1 at 32 registers and full
+// occupancy wins — 0.162 ms, 4.74 TB/s of algorithmic traffic = 72 % of the measured HBM copy peak — over
+// U = 2 (0.181), 4 (0.213), 8 (0.293).
+#ifndef POLICY_U2
+#define POLICY_U2 1   // nodes per thread and trip, n = 2: occupancy beats per-thread memory parallelism (profiles/r01E_policy_variants.txt)
+#endif
+#ifndef POLICY_U4
+#define POLICY_U4 1   // the same, n = 3 and 4
+#endif
+template <int N, int U>
+__global__ void __launch_bounds__(256)
+sweep_policy_kernel(const __grid_constant__ DevProblem P, const double* __restrict__ Jn, double* __restrict__ Jo,
+                    long long* __restrict__ pi, const double* __restrict__ xnext, const double* __restrict__ Gtab,
+                    unsigned long long* __restrict__ partials, unsigned int* counter, double* __restrict__ stats) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long tstride = (long long)gridDim.x * blockDim.x;
+    Stats3 st = stats_identity();
+    for (long long first = P.node_begin; first < P.node_end; first += tstride * U) {
+        double x[U][N], g[U], jn[U];
+        bool act[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long node = first + u * tstride + tid;
+            act[u] = node < P.node_end;
+            if (act[u]) {
+                const long long slot = node - P.slab_node_begin;   // row of the (slab-local) tables
+                const double2* __restrict__ xr = (const double2*)(xnext + slot * N);   // N even: 16-byte aligned rows
+                if (N % 2 == 0) {
+#pragma unroll
+                    for (int d = 0; d < N; d += 2) {
+                        const double2 v = __ldcs(xr + d / 2);
+                        x[u][d] = v.x; x[u][d + 1] = v.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int d = 0; d < N; ++d) x[u][d] = __ldcs(xnext + slot * N + d);
+                }
+                g[u] = __ldcs(Gtab + slot);
+                jn[u] = __ldg(Jn + node);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (act[u]) {
+                const long long node = first + u * tstride + tid;
+                bool oob;
+                const double Jx = rgi_linear<N>(P, Jn, x[u], oob);
+                const double Q = g[u] + P.alpha * Jx;
+                Jo[node] = Q;
+                pi[node] = 0;
+                const double d = Q - jn[u];
+                Stats3 mine;
+                mine.jmax = Q; mine.dmax = d; mine.dmin = d;
+                stats_merge(st, mine);
+            }
+        }
     }
     block_stats_finish(st, partials, counter, stats);
 }
@@ -239,6 +320,7 @@ struct pdp_handle {
     double* d_xnext = nullptr;
     double* d_G = nullptr;
     bool have_J = false, have_lut = false, pending = false;
+    bool halo_stale = false;      // pdp_sweep_host on a slab handle: halo planes of J need pdp_exchange_current / pdp_set_J
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -249,6 +331,7 @@ struct pdp_handle {
     size_t smem_bytes = 0;
     int lanes_per_node = 1;       // G of the fused kernels
     int force_lanes = 0;          // test hook (PYRODP_LANES): pin G to 1, 4 or 16
+    int policy_blocks = 0;        // one resident wave of sweep_policy_kernel blocks
     bool pend_mono = false;       // pendulum: x_next[1] is non-decreasing along the action list (see sweep_fused.cuh, MONO)
     bool force_generic = false;   // test hook (PYRODP_GENERIC=1): use the order-agnostic action loop anyway
     void* fused = nullptr;        // selected fused kernel instantiation
@@ -708,6 +791,7 @@ extern "C" int pdp_set_J(pdp_handle* h, const double* J_host) {
                                     h->alloc_nodes() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->have_J = true;
+    h->halo_stale = false;
     return PDP_OK;
 }
 
@@ -786,10 +870,29 @@ static int launch_planes(pdp_handle* h, int p0, int p1, int stat_set, double* st
     }
     if (P.system_id == PDP_SYS_LUT) {
         if (!h->have_lut) return fail(h, PDP_ESTATE, "pdp_sweep: LUT mode needs pdp_set_lut first");
+        if (P.A == 1) {   // policy evaluation: the streaming kernel
+            typedef void (*policy_kernel_t)(const DevProblem, const double*, double*, long long*, const double*, const double*,
+                                            unsigned long long*, unsigned int*, double*);
+            policy_kernel_t pk = P.n == 2 ? (policy_kernel_t)sweep_policy_kernel<2, POLICY_U2>
+                               : P.n == 3 ? (policy_kernel_t)sweep_policy_kernel<3, POLICY_U4> : (policy_kernel_t)sweep_policy_kernel<4, POLICY_U4>;
+            if (h->policy_blocks == 0) {
+                int per_sm = 0, sm_count = 148;
+                cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
+                CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)pk, 256, 0));
+                h->policy_blocks = std::max(per_sm, 1) * sm_count;
+            }
+            const long long blocks = std::min<long long>((nodes + 256 - 1) / 256, h->policy_blocks);
+            pk<<<(unsigned)blocks, 256, 0, stream>>>(P, Jn, Jo, h->piv(), h->d_xnext, h->d_G, slots, counter, stats);
+            CUDA_TRY(h, cudaGetLastError());
+            h->launches += 1;
+            return PDP_OK;
+        }
         int G = 1;
         while (G < 32 && G < P.A) G <<= 1;
-        const long long blocks = (nodes * G + SWEEP_THREADS - 1) / SWEEP_THREADS;
-        if (blocks > 0x7fffffffLL) return fail(h, PDP_ENOTSUP, "grid too large for one launch");
+        int sm_count = 148;
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
+        // about one resident wave (12 blocks of 128 threads per SM at 40-56 registers) strides over the nodes
+        const long long blocks = std::min<long long>((nodes * G + SWEEP_THREADS - 1) / SWEEP_THREADS, (long long)sm_count * 12);
         if (P.n == 2) launch_lut<2>(h, stream, P, G, (unsigned)blocks, Jn, Jo, slots, counter, stats);
         else if (P.n == 3) launch_lut<3>(h, stream, P, G, (unsigned)blocks, Jn, Jo, slots, counter, stats);
         else launch_lut<4>(h, stream, P, G, (unsigned)blocks, Jn, Jo, slots, counter, stats);
@@ -1003,6 +1106,7 @@ extern "C" int pdp_sweep_enqueue(pdp_handle* h) {
     CHECK_HANDLE(h);
     if (!h->have_J) return fail(h, PDP_ESTATE, "pdp_sweep: no cost-to-go yet (pdp_set_J / pdp_eval_terminal_cost)");
     if (h->pending) return fail(h, PDP_ESTATE, "pdp_sweep: an async sweep is pending");
+    if (h->halo_stale) return fail(h, PDP_ESTATE, "pdp_sweep: the halo planes are stale after pdp_sweep_host on a slab; call pdp_exchange_current or pdp_set_J");
     const bool sharded = h->comm && h->world > 1;
     if (!sharded && h->slab_nodes() != h->N)
         return fail(h, PDP_ESTATE, "pdp_sweep: handle owns a slab only; attach a communicator (pdp_comm_init) or drive it with "
@@ -1084,9 +1188,13 @@ extern "C" int pdp_sweep(pdp_handle* h, int32_t n_sweeps, pdp_stats* stats_out) 
 // returns, and the per-chunk statistics land in the handle's pinned host buffer.  Runs either directly or
 // under stream capture (then nothing executes and the work becomes a CUDA graph).
 static int host_pipeline_enqueue(pdp_handle* h, const double* J_next_host, double* J_host, int64_t* pi_host, int C) {
-    std::vector<int> bound(C + 1);
-    for (int i = 0; i <= C; ++i) bound[i] = (int)((long long)i * h->n0 / C);
-    double* Jc = h->dJ[h->cur_idx];
+    // upload chunks partition the planes the handle holds (slab + halo), backup chunks the planes it computes
+    std::vector<int> ub(C + 1), sb(C + 1);
+    for (int i = 0; i <= C; ++i) {
+        ub[i] = h->alloc_begin + (int)((long long)i * (h->alloc_end - h->alloc_begin) / C);
+        sb[i] = h->slab_begin + (int)((long long)i * (h->slab_end - h->slab_begin) / C);
+    }
+    double* Jc = h->dJ[h->cur_idx];       // element 0 = plane alloc_begin
     double* Jw = h->dJ[1 - h->cur_idx];
     // uploads start once earlier work of the handle's stream (which may read J[cur]) is done
     CUDA_TRY(h, cudaEventRecord(h->ev_start, h->stream));
@@ -1099,25 +1207,27 @@ static int host_pipeline_enqueue(pdp_handle* h, const double* J_next_host, doubl
     const int K = std::min(3, C);
     for (int i = 1; i < K; ++i) CUDA_TRY(h, cudaStreamWaitEvent(cs[i], h->ev_start, 0));
     for (int i = 0; i < C; ++i) {
-        const size_t off = (size_t)bound[i] * h->plane, cnt = (size_t)(bound[i + 1] - bound[i]) * h->plane;
-        if (cnt) CUDA_TRY(h, cudaMemcpyAsync(Jc + off, J_next_host + off, cnt * sizeof(double), cudaMemcpyHostToDevice, h->h2d_stream));
+        const size_t cnt = (size_t)(ub[i + 1] - ub[i]) * h->plane;
+        if (cnt) CUDA_TRY(h, cudaMemcpyAsync(Jc + (size_t)(ub[i] - h->alloc_begin) * h->plane, J_next_host + (size_t)ub[i] * h->plane,
+                                             cnt * sizeof(double), cudaMemcpyHostToDevice, h->h2d_stream));
         CUDA_TRY(h, cudaEventRecord(h->ev_up[i], h->h2d_stream));
     }
     int waited[3] = {-1, -1, -1};  // uploads [0..waited] are already ordered before that compute stream
     for (int i = 0; i < C; ++i) {
-        // the chunk's backups read planes < bound[i+1] + halo_hi (and > bound[i] - halo_lo: uploaded earlier)
-        const int top = std::min(h->n0, bound[i + 1] + h->halo_hi) - 1;
-        int need = i;
-        while (need + 1 < C && bound[need + 1] <= top) ++need;
+        // the chunk's backups read planes < sb[i+1] + halo_hi (and >= sb[i] - halo_lo: uploaded earlier, uploads are in order)
+        const int top = std::min(h->alloc_end, sb[i + 1] + h->halo_hi) - 1;
+        int need = 0;
+        while (need + 1 < C && ub[need + 1] <= top) ++need;
         const int si = i % K;
         if (need > waited[si]) { CUDA_TRY(h, cudaStreamWaitEvent(cs[si], h->ev_up[need], 0)); waited[si] = need; }
-        int rc = launch_planes(h, bound[i], bound[i + 1], si, h->dchunk_stats + 3 * i, cs[si]);
+        int rc = launch_planes(h, sb[i], sb[i + 1], si, h->dchunk_stats + 3 * i, cs[si]);
         if (rc != PDP_OK) return rc;
         CUDA_TRY(h, cudaEventRecord(h->ev_done[i], cs[si]));
         CUDA_TRY(h, cudaStreamWaitEvent(h->d2h_stream, h->ev_done[i], 0));
-        const size_t off = (size_t)bound[i] * h->plane, cnt = (size_t)(bound[i + 1] - bound[i]) * h->plane;
+        const size_t off = (size_t)(sb[i] - h->slab_begin) * h->plane, cnt = (size_t)(sb[i + 1] - sb[i]) * h->plane;
         if (cnt) {
-            CUDA_TRY(h, cudaMemcpyAsync(J_host + off, Jw + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->d2h_stream));
+            CUDA_TRY(h, cudaMemcpyAsync(J_host + off, Jw + (size_t)(sb[i] - h->alloc_begin) * h->plane, cnt * sizeof(double),
+                                        cudaMemcpyDeviceToHost, h->d2h_stream));
             CUDA_TRY(h, cudaMemcpyAsync(pi_host + off, h->dpi + off, cnt * sizeof(long long), cudaMemcpyDeviceToHost, h->d2h_stream));
         }
     }
@@ -1143,12 +1253,12 @@ static bool is_pinned_host(const void* p) {
 extern "C" int pdp_sweep_host(pdp_handle* h, const double* J_next_host, double* J_host, int64_t* pi_host, pdp_stats* stats_out) {
     CHECK_HANDLE(h);
     if (!J_next_host || !J_host || !pi_host) return fail(h, PDP_EINVAL, "pdp_sweep_host: null pointer");
-    if (h->comm || h->slab_nodes() != h->N) return fail(h, PDP_ESTATE, "pdp_sweep_host: the handle must own the whole grid (single GPU)");
+    if (h->slab_end <= h->slab_begin) return fail(h, PDP_ESTATE, "pdp_sweep_host: this handle computes no planes");
     if (h->enqueued || h->pending) return fail(h, PDP_ESTATE, "pdp_sweep_host: collect / commit the outstanding sweeps first");
     if (h->P.system_id == PDP_SYS_LUT && !h->have_lut) return fail(h, PDP_ESTATE, "pdp_sweep: LUT mode needs pdp_set_lut first");
     int C = 8;
     if (const char* env = getenv("PYRODP_HOST_CHUNKS")) C = atoi(env);
-    C = std::max(1, std::min(std::min(C, PDP_HOST_MAX_CHUNKS), h->n0));
+    C = std::max(1, std::min(std::min(C, PDP_HOST_MAX_CHUNKS), h->slab_end - h->slab_begin));
     if (!h->h2d_stream) {
         CUDA_TRY(h, cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
         CUDA_TRY(h, cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
@@ -1219,6 +1329,8 @@ extern "C" int pdp_sweep_host(pdp_handle* h, const double* J_next_host, double* 
         if (rc != PDP_OK) return rc;
     }
     h->cur_idx = 1 - h->cur_idx;
+    // a slab handle has just rewritten its own planes only: the halo copies of the new J are its neighbours' to give
+    h->halo_stale = h->slab_nodes() != h->N;
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     if (stats_out) {
         const double* cst = h->h_chunk_stats;
@@ -1238,6 +1350,7 @@ extern "C" int pdp_exchange_current(pdp_handle* h) {
     CHECK_HANDLE(h);
     int rc = exchange(h, h->cur_idx, h->stream);
     if (rc != PDP_OK) return rc;
+    if (h->comm && h->world > 1) h->halo_stale = false;
     if (h->exchange_mode == 3 && h->world > 1) {
         halo_wait_kernel<<<1, 1, 0, h->stream>>>(h->dflags, h->peer_seq, h->rank > 0, h->rank < h->world - 1, h->dflags + 3,
                                                  20000000000LL);

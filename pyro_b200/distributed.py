@@ -222,6 +222,12 @@ class ShardedEngine:
         self.eng.commit_sweep()
         return torch.stack([used[:, 0].max(), used[:, 1].max(), -(used[:, 2].min())])
 
+    def sweep_host(self, J_next, J_out=None, pi_out=None):
+        """One sweep with host arrays: J_next is the full (N,) array, J_out / pi_out receive THIS RANK'S slab.
+        The rank uploads the planes it holds (slab + halo) and needs no exchange for this one sweep; the
+        statistics returned are those of the slab."""
+        return self.eng.sweep_host(J_next, J_out, pi_out)
+
     def sweep_nowait(self):
         """Enqueue one sweep + exchange without any host synchronisation; pair with collect_stats()."""
         if self.backend == "native":

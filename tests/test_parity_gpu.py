@@ -97,6 +97,50 @@ def test_lut_mode_3d_generic_system():
     J_ref, pi_ref = npo.lut_sweep(levels, dims, J0, x_next, G, 0.97, use_scipy=True)
     assert np.array_equal(eng.get_J(), J_ref) and np.array_equal(eng.get_pi(), pi_ref)
     eng.close()
+    # one column per node (policy evaluation, dynamicprogramming.py:743-752): the streaming kernel, n = 3
+    pe = Engine(problem.extract(Grid3(), Cost3(), 0.97, lut_actions=1))
+    pe.set_lut(x_next[:, 2:3, :], G[:, 2:3])
+    pe.set_J(J0)
+    st = pe.sweep(2)
+    J1, _ = npo.lut_sweep(levels, dims, J0, x_next[:, 2:3, :], G[:, 2:3], 0.97, use_scipy=True)
+    J2, _ = npo.lut_sweep(levels, dims, J1, x_next[:, 2:3, :], G[:, 2:3], 0.97, use_scipy=True)
+    assert np.array_equal(pe.get_J(), J2) and (pe.get_pi() == 0).all() and st[1, 0] == J2.max() and st[1, 1] == (J2 - J1).max()
+    pe.close()
+
+
+@pytest.mark.parametrize("n", [2, 4])
+def test_policy_kernel_on_a_large_grid_equals_numpy_restatement(n):
+    """The streaming policy-evaluation kernel at a size with many trips per thread and a ragged tail."""
+    rng = np.random.default_rng(9)
+    dims = (307, 293) if n == 2 else (23, 19, 21, 17)
+    levels = [np.linspace(-1.0 - d, 2.0 + d, dims[d]) for d in range(n)]
+    N = int(np.prod(dims))
+    X = np.stack([g.reshape(-1) for g in np.meshgrid(*levels, indexing="ij")], axis=1)
+    step = np.array([levels[d][1] - levels[d][0] for d in range(n)])
+    x_next = X[:, None, :] + rng.uniform(-2.2, 2.2, (N, 1, n)) * step
+    G = rng.uniform(0, 2, (N, 1))
+
+    class SysN:
+        m = 1
+        x_lb, x_ub = np.array([l[0] for l in levels]), np.array([l[-1] for l in levels])
+        u_lb, u_ub = np.array([-1.0]), np.array([1.0])
+    SysN.n = n
+
+    class GridN:
+        sys, dt = SysN(), 0.05
+        x_grid_dim, u_grid_dim = np.array(dims), np.array([3])
+        x_level, u_level = levels, [np.linspace(-1, 1, 3)]
+
+    class CostN:
+        INF = 50.0
+    eng = Engine(problem.extract(GridN(), CostN(), 0.9, lut_actions=1))
+    eng.set_lut(x_next, G)
+    J0 = rng.uniform(0, 100, N)
+    eng.set_J(J0)
+    eng.sweep(1)
+    J_ref, _ = npo.lut_sweep(levels, list(dims), J0, x_next, G, 0.9, use_scipy=False)
+    assert np.array_equal(eng.get_J(), J_ref)
+    eng.close()
 
 
 MID = {
@@ -355,6 +399,14 @@ def test_host_array_sweep_is_the_same_backup(name, chunks, pinned, monkeypatch):
     with pytest.raises(ValueError):
         eng.sweep_host(J0[:-1])
     eng.close()
+    # slab handles (what each rank of a multi-GPU run holds): full J_next in, the slab's J / pi out, no exchange needed
+    n0 = P.dims[0]
+    plane = P.N // n0
+    for b, e in ((0, n0 // 3), (n0 // 3, 2 * n0 // 3 + 1), (2 * n0 // 3 + 1, n0)):
+        slab = Engine(problem.extract(grid, cf, case.get("alpha", 1.0), slab=(b, e)))
+        Js, pis, _ = slab.sweep_host(host(J0.copy()), host(np.empty((e - b) * plane)), host(np.empty((e - b) * plane, dtype=np.int64)))
+        assert np.array_equal(Js, J_ref[b * plane:e * plane]) and np.array_equal(pis, pi_ref[b * plane:e * plane]), (b, e)
+        slab.close()
 
 
 @pytest.mark.parametrize("name", list(POLICY_CASES))
