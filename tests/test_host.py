@@ -204,3 +204,16 @@ def test_slab_partition():
         covered = [p for b, e, _ in slabs for p in range(b, e)]
         assert covered == list(range(n0))
         assert all(b == min(r * per, n0) for r, (b, e, _) in enumerate(slabs))
+
+
+def test_product_package_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under pyro_b200/ (Python or CUDA) may import, include or execute it."""
+    import re
+    pkg = os.path.join(ROOT, "pyro_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(base, f), encoding="utf-8").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert not re.search(r"#include\s+[\"<][^\">]*oracle", src), f
+                assert "dp_oracle" not in src and "np_oracle" not in src and "c_oracle" not in src, f

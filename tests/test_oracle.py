@@ -149,3 +149,29 @@ def test_policy_evaluation_oracle_and_mirror_tables_match_reference(name):
                                             engine_factory=lambda dp, P: NoEngine(grid.nodes_n))
     pe.compute_lookuptable()
     assert np.array_equal(pe.x_next_table, gold["x_next_table"]) and np.array_equal(pe.G, gold["G"])
+
+
+@pytest.mark.parametrize("name", ["pend_51x51x11", "pend_101x101x21", "cartpole_swingup"])
+def test_boundary_audit_near_the_domain_bounds(name):
+    """SURVEY.md section 7, hard part 1: pi hinges on the in/out-of-box classification of x_next within an ulp of
+    the bounds.  Count the sampled pairs that land exactly on / within 4 ulp of a bound and check that the
+    restatement classifies every one of them as the reference did (strict compares: ON the bound is inside)."""
+    case, gold = CASES[name], load_golden(name)
+    grid, cost = oracle_objects(case)
+    stride = int(gold["table_stride"])
+    x_next, x_ok, _, _ = grid.tables(cost)
+    x_next, x_ok = x_next[::stride], x_ok[::stride]
+    lb, ub = np.asarray(grid.spec.x_lb, float), np.asarray(grid.spec.x_ub, float)
+    near = np.zeros(x_next.shape[:2], dtype=bool)
+    on = np.zeros_like(near)
+    for d in range(x_next.shape[2]):
+        for b in (lb[d], ub[d]):
+            dist = np.abs(x_next[..., d] - b)
+            near |= dist <= 4 * np.spacing(abs(b))
+            on |= x_next[..., d] == b
+    print(f"{name}: {int(on.sum())} pairs exactly on a bound, {int(near.sum())} within 4 ulp, of {near.size}")
+    assert np.array_equal(x_ok[near], gold["x_next_isok_sample"][near])
+    if name == "pend_51x51x11":
+        assert on.sum() > 0                      # e.g. dq = 0 nodes on the q boundary
+    inside_otherwise = np.all((x_next >= lb) & (x_next <= ub), axis=-1)
+    assert (x_ok[on] == inside_otherwise[on]).all()   # a pair ON one bound is valid unless another axis is outside
