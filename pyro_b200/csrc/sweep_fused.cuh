@@ -173,6 +173,7 @@ sweep_pendulum_kernel(const __grid_constant__ DevProblem P, const double* __rest
         // Two actions per iteration under one compare and one warp vote.  evalq = evaluate_linear_2d in
         // its value-first association on the cached products, Q = g*dt + alpha*J
         // (dynamicprogramming.py:223): 15 FP64 issues.
+        double gxv = gx;
         auto evalq = [&](double x, double gu) {
             const double y1 = exact_div(x - lo, den, rinv);
             const double omy1 = 1.0 - y1;
@@ -180,7 +181,7 @@ sweep_pendulum_kernel(const __grid_constant__ DevProblem P, const double* __rest
             Jx = Jx + p01 * y1;
             Jx = Jx + p10 * omy1;
             Jx = Jx + p11 * y1;
-            return (gx + gu) * dt_cost + (ALPHA1 ? Jx : alpha * Jx);
+            return (gxv + gu) * dt_cost + (ALPHA1 ? Jx : alpha * Jx);
         };
         // x reached the top of the cached cell (or there is none yet): isavalidstate (system.py:198-205),
         // then walk the level table upwards — the interval scipy's search returns — and gather the corners
@@ -189,11 +190,11 @@ sweep_pendulum_kernel(const __grid_constant__ DevProblem P, const double* __rest
             if (!(x < hi)) {
                 const double lb1 = P.lb[1], ub1 = P.ub[1];
                 if (!(x <= ub1)) {
-                    // above the box, and so is every later action: park the lane on an all-covering
-                    // cell whose products are +inf, so that its Q (inf or NaN) never wins again
+                    // above the box, and so is every later action: park the lane on an all-covering cell
+                    // with an infinite state cost, so that its Q (inf, or NaN when dt_cost is 0) never wins again
                     oob = true;
                     hi = PINF;
-                    p00 = p01 = p10 = p11 = PINF;
+                    gxv = PINF;
                 } else if (x < lb1) {
                     oob = true;    // still below the box
                 } else {
