@@ -60,6 +60,13 @@ class LookUpTableController:
     def c(self, y, r, t=0):
         return self.lookup_table_selection(y)
 
+    # StaticController conveniences (pyro/control/controller.py:93-155): constant reference, feedback at it
+    def t2r(self, t):
+        return self.rbar
+
+    def cbar(self, y, t=0):
+        return self.c(y, self.rbar, t)
+
 
 class DynamicProgramming:
     """Dynamic programming on a grid sys — Bellman sweeps on the GPU."""

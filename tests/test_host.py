@@ -217,3 +217,51 @@ def test_product_package_never_touches_the_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
                 assert not re.search(r"#include\s+[\"<][^\">]*oracle", src), f
                 assert "dp_oracle" not in src and "np_oracle" not in src and "c_oracle" not in src, f
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference not present (GPU box)")
+@pytest.mark.parametrize("name", ["pend_time_41x61x7", "cartpole_swingup"])
+def test_grid_mirror_host_methods_equal_the_real_reference(name, tmp_path):
+    """The callers either side of the sweep (discretizer.py:314-664): dense tables, their .npz format, the
+    state/input <-> index conversions and the 2-D slice, on the mirror vs the unmodified reference, bit for bit."""
+    import importlib
+    gen = importlib.import_module("oracle.gen_golden")
+    ns = ref_loader.load()
+    dims = [6, 5] if len(CASES[name]["x_grid_dim"]) == 2 else [4, 5, 3, 4]
+    case = dict(CASES[name], x_grid_dim=dims)
+    with ref_loader.quiet():
+        rsys, rgrid, _, _ = gen.build_reference(ns, case)
+        rgrid.compute_nearest_snext_table()
+    _, grid, _ = build_case(case, lookup=True)
+    grid.compute_nearest_snext_table()
+    for attr in ("x_next_table", "x_next_isok", "action_isok", "s_next_table", "state_from_node_id", "index_from_node_id",
+                 "node_id_from_index", "input_from_action_id", "index_from_action_id", "action_id_from_index"):
+        assert np.array_equal(getattr(grid, attr), getattr(rgrid, attr)), attr
+    rng = np.random.default_rng(4)
+    for _ in range(50):
+        x = rng.uniform(rsys.x_lb - 1.0, rsys.x_ub + 1.0)
+        u = rng.uniform(rsys.u_lb - 1.0, rsys.u_ub + 1.0)
+        assert np.array_equal(grid.get_index_from_state(x), rgrid.get_index_from_state(x))
+        assert np.array_equal(grid.get_nearest_index_from_state(x), rgrid.get_nearest_index_from_state(x))
+        assert grid.get_nearest_node_id_from_state(x) == rgrid.get_nearest_node_id_from_state(x)
+        assert np.array_equal(grid.get_index_from_input(u), rgrid.get_index_from_input(u))
+        assert np.array_equal(grid.get_nearest_index_from_input(u), rgrid.get_nearest_index_from_input(u))
+        assert grid.get_nearest_action_id_from_input(u) == rgrid.get_nearest_action_id_from_input(u)
+    Z = rng.uniform(0, 1, grid.nodes_n)
+    for a1, a2 in ((0, 1),) if len(dims) == 2 else ((0, 1), (1, 3), (2, 0), (3, 2)):
+        want = rgrid.get_2D_slice_of_grid(rgrid.get_grid_from_array(Z), a1, a2)
+        assert np.array_equal(grid.get_2D_slice_of_grid(grid.get_grid_from_array(Z), a1, a2), want), (a1, a2)
+    # on-disk format: written by one side, read by the other
+    grid.save_lookup_tables(str(tmp_path / "mine"))
+    rgrid.x_next_table = None
+    rgrid.load_lookup_tables(str(tmp_path / "mine"))
+    assert np.array_equal(rgrid.x_next_table, grid.x_next_table) and np.array_equal(rgrid.action_isok, grid.action_isok)
+    rgrid.save_lookup_tables(str(tmp_path / "theirs"))
+    _, fresh, _ = build_case(case)
+    fresh.load_lookup_tables(str(tmp_path / "theirs"))
+    assert np.array_equal(fresh.x_next_table, grid.x_next_table) and np.array_equal(fresh.x_next_isok, grid.x_next_isok)
+    if len(dims) == 2:
+        J = rng.uniform(0, 1, grid.nodes_n)
+        p = np.array([[0.3, -0.2], [1.1, 0.7]])
+        assert np.array_equal(grid.compute_bivariatespline_2D_interpolation_function(J).ev(p[:, 0], p[:, 1]),
+                              rgrid.compute_bivariatespline_2D_interpolation_function(J).ev(p[:, 0], p[:, 1]))
