@@ -423,6 +423,9 @@ def main():
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_eval": b_eval(n, A),
                 "algorithmic_bytes_per_launch": slab_evals * b_eval(n, A),
                 "compulsory_dram_bytes_per_launch": 24.0 * N / world,
+                "dram": {"achieved": (ncu_traffic(args.workload) or 24.0 * N / world) / (kernel_ms * 1e-3) / 1e9, "unit": "GB/s",
+                         "frac": (ncu_traffic(args.workload) or 24.0 * N / world) / (kernel_ms * 1e-3) / 1e9 / peak,
+                         "note": "measured DRAM bytes per launch (ncu) over this run's kernel time: the sweep is not HBM-bound"},
                 "binding_resource": issue_model(kernel_eng.problem.system_id, slab_evals, kernel_ms, clocks),
                 "note": "contract figure of SURVEY 8(d): the 2^n-corner J gather is served by L1/L2, so DRAM traffic is ~24 B/node "
                         "and frac can exceed 1; the binding resource is the FP64 pipe (see DESIGN.md, profiles/)"}
