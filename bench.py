@@ -65,7 +65,7 @@ def ncu_traffic(workload):
 def issue_model(system_id, evals, kernel_ms, clocks):
     """What actually bounds the sweep: an FP64 warp instruction holds a sub-partition's issue
     port for two cycles (scripts/micro/fp64_peak.cu, profiles/r01_fp64_peak_micro.txt), so a warp costs
-    2*FP64 + other instructions.  Instruction counts per warp-eval are ncu's (profiles/r01l / r01x source page);
+    2*FP64 + other instructions.  Instruction counts per warp-eval are ncu's (source page of profiles/r01K);
     the measured cycles come from this run's kernel time."""
     if system_id != 1:
         return {"resource": "issue port + L1 data pipe (see DESIGN.md section 5, profiles/r01b_cp101.txt)"}
@@ -73,12 +73,12 @@ def issue_model(system_id, evals, kernel_ms, clocks):
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     mhz = (clocks or {}).get("sm_mhz") or 1965.0
     measured = kernel_ms * 1e-3 * mhz * 1e6 * sms * 4 / (evals / 32.0)
-    f64, other = 19.45, 21.15
+    f64, other = 19.45, 18.63
     return {"resource": "issue port: FP64 warp instructions take 2 issue cycles", "fp64_inst_per_warp_eval": f64,
             "other_inst_per_warp_eval": other, "model_cycles_per_warp_eval": 2 * f64 + other,
             "measured_cycles_per_warp_eval": measured, "frac_of_issue_limit": (2 * f64 + other) / measured,
             "arithmetic_floor_cycles_per_warp_eval": 2 * 17.5 + 3.0,
-            "source": "profiles/r01l (ncu source page counts), profiles/r01_fp64_peak_micro.txt"}
+            "source": "profiles/r01K_cfg2 (ncu source page counts of the final kernel), profiles/r01_fp64_peak_micro.txt"}
 
 
 def weak_scaled(case, world):

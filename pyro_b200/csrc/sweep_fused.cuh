@@ -96,8 +96,8 @@ __device__ __forceinline__ void stage(double* dst, const double* __restrict__ sr
 // stay in registers until x_next[1] leaves the cell: the common action costs 19 FP64 issues (17.5 in the
 // MONO loop), one LDS and no global load; leaving the cell re-runs the table-checked search and four
 // gathers.  An FP64 instruction holds the SM sub-partition's issue port for two cycles (measured,
-// scripts/micro/fp64_peak.cu), so the kernel's cost is 2*FP64 + other instructions per warp: ncu r01l
-// counts 19.5 + 21.2 per warp-eval = 60 cycles, and the measured 0.324 ms/sweep at cfg 2 IS 60 cycles.
+// scripts/micro/fp64_peak.cu), so the kernel's cost is 2*FP64 + other instructions per warp: ncu r01K
+// counts 19.45 + 18.63 per warp-eval = 57.5 cycles, and the measured 0.312 ms/sweep at cfg 2 IS 57.7 cycles.
 // =================================================================================================
 // MONO = the host verified that x_next[1] cannot decrease along the action list (B.u ascending,
 // inv(H) > 0, dt > 0, every action allowed — the linspace input grid of a pendulum): then lo <= x
