@@ -6,7 +6,8 @@ a C ABI (``include/pyrodp.h``); this package is the thin host-side mirror of the
 Python interface for that path.
 """
 from . import costfunction, discretizer, dynamicprogramming, systems  # noqa: F401
-from .dynamicprogramming import DynamicProgramming, DynamicProgrammingWithLookUpTable  # noqa: F401
+from .dynamicprogramming import (DynamicProgramming, DynamicProgrammingWithLookUpTable, LookUpTableController,  # noqa: F401
+                                 PolicyEvaluator, PolicyEvaluatorWithLookUpTable)
 from .discretizer import GridDynamicSystem  # noqa: F401
 
 __version__ = "0.1.0"
