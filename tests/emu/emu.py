@@ -1,0 +1,38 @@
+"""ctypes access to tests/emu/libpyrodp_emu.so — the product's fused kernels compiled for and run on the CPU.
+TEST INFRASTRUCTURE ONLY (see tests/emu/cuda_emu.h)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "libpyrodp_emu.so")
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        srcs = [os.path.join(HERE, f) for f in ("emu_main.cpp", "cuda_emu.h", "build.sh")]
+        root = os.path.dirname(os.path.dirname(HERE))
+        srcs += [os.path.join(root, "pyro_b200", "csrc", f) for f in ("pyrodp_device.cuh", "sweep_fused.cuh")]
+        if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
+            subprocess.check_call(["bash", os.path.join(HERE, "build.sh")])
+        _lib = C.CDLL(LIB)
+        _lib.emu_sweep.restype = C.c_int
+        _lib.emu_sweep.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    return _lib
+
+
+def sweep(problem, J_next, lanes=1, force_generic=False):
+    """One backup of the whole grid by the emulated kernel: (J, pi, [j_max, delta_max, delta_min])."""
+    J_next = np.ascontiguousarray(J_next, dtype=np.float64)
+    J = np.empty(problem.N)
+    pi = np.empty(problem.N, dtype=np.int64)
+    stats = np.empty(3)
+    rc = load().emu_sweep(C.addressof(problem.c), J_next.ctypes.data, J.ctypes.data, pi.ctypes.data, stats.ctypes.data,
+                          int(lanes), int(bool(force_generic)))
+    if rc != 0:
+        raise RuntimeError(f"emu_sweep failed ({rc})")
+    return J, pi, stats

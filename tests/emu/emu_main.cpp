@@ -1,0 +1,224 @@
+// CPU run of the product's fused sweep kernels (TEST INFRASTRUCTURE ONLY; see cuda_emu.h).
+//   build: tests/emu/build.sh  ->  tests/emu/libpyrodp_emu.so
+// Entry point: emu_sweep(const pdp_problem*, J_next, J, pi, stats, lanes, force_generic) — the same descriptor the
+// CUDA library takes (include/pyrodp.h), one sweep of the whole grid.
+#include "cuda_emu.h"
+
+#include <algorithm>
+#include <string>
+
+#include "../../include/pyrodp.h"
+
+#include <stdexcept>
+
+emu_uint3 threadIdx, blockIdx, blockDim, gridDim;
+EmuBlock* emu_block = nullptr;
+double smem[32 * 1024] __attribute__((aligned(16)));   // the dynamic shared memory of the running block (256 KB)
+
+// ---- coroutines: a minimal x86-64 System V context switch (callee-saved registers + stack pointer) --------------
+extern "C" void emu_switch(void** save_sp, void* load_sp);
+asm(R"(
+.text
+.globl emu_switch
+.type emu_switch,@function
+emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size emu_switch,.-emu_switch
+)");
+
+namespace {
+struct Co {
+    void* sp = nullptr;
+    bool done = false;
+    EmuGroup* wait_group = nullptr;     // parked at a barrier of this group ...
+    unsigned long long wait_gen = 0;    // ... until its generation moves past this value
+    emu_uint3 tid{};
+};
+constexpr size_t kStack = 256 * 1024;
+std::vector<Co> g_co;
+std::vector<char> g_stacks;
+void* g_sched_sp = nullptr;
+int g_cur = -1;
+const std::function<void()>* g_body = nullptr;
+
+void co_yield_to_scheduler() { emu_switch(&g_co[g_cur].sp, g_sched_sp); }
+
+void co_entry() {
+    (*g_body)();
+    g_co[g_cur].done = true;
+    co_yield_to_scheduler();
+    __builtin_trap();   // a finished coroutine is never resumed
+}
+}  // namespace
+
+void emu_barrier(EmuGroup& g) {
+    if (++g.arrived == g.size) {        // last to arrive: release everybody, go on
+        g.arrived = 0;
+        ++g.generation;
+        return;
+    }
+    Co& me = g_co[g_cur];
+    me.wait_group = &g;
+    me.wait_gen = g.generation;
+    co_yield_to_scheduler();            // resumed by the scheduler once the generation has moved
+    me.wait_group = nullptr;
+}
+
+void emu_launch(emu_uint3 grid, emu_uint3 block, const std::function<void()>& body) {
+    const int nthreads = (int)(block.x * block.y * block.z);
+    if (nthreads % 32) throw std::runtime_error("emulator: block size must be a multiple of 32");
+    blockDim = block;
+    gridDim = grid;
+    g_body = &body;
+    g_stacks.assign((size_t)nthreads * kStack + 64, 0);
+    for (unsigned bz = 0; bz < grid.z; ++bz)
+        for (unsigned by = 0; by < grid.y; ++by)
+            for (unsigned bx = 0; bx < grid.x; ++bx) {
+                EmuBlock blk;
+                blk.all.size = nthreads;
+                blk.warps.resize(nthreads / 32);
+                for (auto& w : blk.warps) w.size = 32;
+                emu_block = &blk;
+                blockIdx = {bx, by, bz};
+                g_co.assign(nthreads, Co());
+                for (int t = 0; t < nthreads; ++t) {
+                    uintptr_t top = ((uintptr_t)(g_stacks.data() + (size_t)(t + 1) * kStack)) & ~(uintptr_t)15;
+                    void** sp = (void**)(top - 64);          // 6 callee-saved registers, entry address, dummy return
+                    for (int i = 0; i < 8; ++i) sp[i] = nullptr;
+                    sp[6] = (void*)&co_entry;
+                    g_co[t].sp = sp;
+                    g_co[t].tid = {(unsigned)t % block.x, ((unsigned)t / block.x) % block.y, (unsigned)t / (block.x * block.y)};
+                }
+                int remaining = nthreads;
+                while (remaining > 0) {
+                    bool progressed = false;
+                    for (int t = 0; t < nthreads; ++t) {
+                        Co& c = g_co[t];
+                        if (c.done) continue;
+                        if (c.wait_group && c.wait_group->generation == c.wait_gen) continue;   // still parked
+                        g_cur = t;
+                        threadIdx = c.tid;
+                        emu_switch(&g_sched_sp, c.sp);
+                        progressed = true;
+                        if (c.done) --remaining;
+                    }
+                    if (!progressed) throw std::runtime_error("emulator: deadlock (a barrier some thread never reaches)");
+                }
+            }
+    emu_block = nullptr;
+    g_body = nullptr;
+}
+
+#include "gen/pyrodp_device.cuh"
+#include "gen/sweep_fused.cuh"
+
+typedef void (*fused_kernel_t)(const DevProblem, const double*, double*, long long*, unsigned long long*, unsigned int*, double*);
+
+template <int G, bool A1>
+static fused_kernel_t fused_for(int system_id, bool nodamp, bool mono) {
+    switch (system_id) {
+        case PDP_SYS_PENDULUM:
+            if (mono) return nodamp ? sweep_pendulum_kernel<G, A1, true, true> : sweep_pendulum_kernel<G, A1, false, true>;
+            return nodamp ? sweep_pendulum_kernel<G, A1, true, false> : sweep_pendulum_kernel<G, A1, false, false>;
+        case PDP_SYS_TWOLINK: return sweep_mech2_kernel<PDP_SYS_TWOLINK, G, A1>;
+        case PDP_SYS_CARTPOLE: return sweep_mech2_kernel<PDP_SYS_CARTPOLE, G, A1>;
+    }
+    return nullptr;
+}
+
+// The device problem exactly as pdp_create lays it out (pyro_b200/csrc/pyrodp.cu), with host pointers.
+struct HostProblem {
+    DevProblem P{};
+    std::vector<std::vector<double>> keep;
+    bool mono = false;
+    const double* hold(const double* src, size_t n) { keep.emplace_back(src, src + n); return keep.back().data(); }
+};
+
+static void fill(const pdp_problem* p, HostProblem& H) {
+    DevProblem& P = H.P;
+    long long N = 1, A = 1;
+    for (int d = 0; d < p->n; ++d) N *= p->dims[d];
+    for (int d = 0; d < p->m; ++d) A *= p->udims[d];
+    P.n = p->n; P.m = p->m; P.dof = p->n / 2; P.A = (int)A;
+    P.system_id = p->system_id; P.cost_id = p->cost_id; P.ontarget_check = p->ontarget_check;
+    P.alpha_is_one = (p->alpha == 1.0);
+    P.dt = p->dt; P.alpha = p->alpha; P.INF = p->INF; P.EPS = p->EPS;
+    long long stride = 1;
+    for (int d = p->n - 1; d >= 0; --d) { P.stride[d] = stride; stride *= p->dims[d]; }
+    P.N = N;
+    const long long plane = N / p->dims[0];
+    P.node_begin = 0; P.node_end = N; P.slab_node_begin = 0; P.plane_begin = 0;
+    (void)plane;
+    for (int d = 0; d < p->n; ++d) {
+        P.dims[d] = p->dims[d];
+        P.lb[d] = p->x_lb[d]; P.ub[d] = p->x_ub[d];
+        P.inv_step[d] = (double)(p->dims[d] - 1) / (p->x_ub[d] - p->x_lb[d]);
+        std::vector<double> rinv(p->dims[d]);
+        for (int i = 0; i + 1 < p->dims[d]; ++i) rinv[i] = 1.0 / (p->x_level[d][i + 1] - p->x_level[d][i]);
+        rinv[p->dims[d] - 1] = 0.0;
+        P.level[d] = H.hold(p->x_level[d], p->dims[d]);
+        P.rinv[d] = H.hold(rinv.data(), rinv.size());
+    }
+    memcpy(P.Q, p->Q, sizeof(P.Q)); memcpy(P.S, p->S, sizeof(P.S));
+    memcpy(P.xbar, p->xbar, sizeof(P.xbar)); memcpy(P.par, p->sys_par, sizeof(P.par));
+    for (int t = 0; t < 4; ++t)
+        if (p->sys_tab[t] && p->sys_tab_len[t] > 0) P.tab[t] = H.hold(p->sys_tab[t], (size_t)p->sys_tab_len[t]);
+    P.all_act_ok = 1;
+    std::vector<double> bu(p->bu, p->bu + (size_t)A * P.dof);
+    for (long long a = 0; a < A; ++a)
+        if (!p->act_ok[a]) {
+            P.all_act_ok = 0;
+            for (int d = 0; d < P.dof; ++d) bu[(size_t)a * P.dof + d] = __builtin_nan("");
+        }
+    if (p->system_id == PDP_SYS_PENDULUM) {
+        bool asc = P.all_act_ok && p->sys_par[0] > 0.0 && p->dt > 0.0;
+        for (long long a = 1; a < A && asc; ++a) asc = bu[a] >= bu[a - 1];
+        H.mono = asc;
+    }
+    P.bu = H.hold(bu.data(), bu.size());
+    P.gu = H.hold(p->gu, (size_t)A);
+}
+
+extern "C" int emu_sweep(const pdp_problem* p, const double* J_next, double* J, long long* pi, double* stats3, int lanes,
+                         int force_generic) {
+    if (!p || p->system_id == PDP_SYS_LUT) return -1;
+    try {
+        HostProblem H;
+        fill(p, H);
+        DevProblem& P = H.P;
+        const int G = lanes;
+        const bool a1 = P.alpha_is_one != 0, nd = (P.system_id == PDP_SYS_PENDULUM) && P.par[1] == 0.0;
+        const bool mono = H.mono && !force_generic;
+        fused_kernel_t k = nullptr;
+        if (G == 1) k = a1 ? fused_for<1, true>(P.system_id, nd, mono) : fused_for<1, false>(P.system_id, nd, mono);
+        else if (G == 4) k = a1 ? fused_for<4, true>(P.system_id, nd, mono) : fused_for<4, false>(P.system_id, nd, mono);
+        else if (G == 16) k = a1 ? fused_for<16, true>(P.system_id, nd, mono) : fused_for<16, false>(P.system_id, nd, mono);
+        if (!k) return -2;
+        emu_uint3 grid, block = {SWEEP_THREADS, 1, 1};
+        if (P.system_id == PDP_SYS_PENDULUM)
+            grid = {(unsigned)P.dims[0], (unsigned)(((long long)P.dims[1] * G + SWEEP_THREADS - 1) / SWEEP_THREADS), 1};
+        else
+            grid = {(unsigned)(P.dims[0] * P.dims[1]),
+                    (unsigned)(((long long)P.dims[2] * P.dims[3] * G + SWEEP_THREADS - 1) / SWEEP_THREADS), 1};
+        std::vector<unsigned long long> slots(3 * STATS_SLOTS, 0);
+        unsigned int counter = 0;
+        emu_launch(grid, block, [&]() { k(P, J_next, J, pi, slots.data(), &counter, stats3); });
+        return 0;
+    } catch (const std::exception&) {
+        return -3;
+    }
+}

@@ -1,0 +1,83 @@
+"""The product's fused sweep kernels, compiled from pyro_b200/csrc/*.cuh with g++ and run on the CPU by the
+coroutine emulator in tests/emu/ (one coroutine per CUDA thread, real barriers / votes / shuffles), against the
+reference fixtures and the C oracle — bit for bit.  This checks the kernels' arithmetic and control flow (cell
+walks, lane splits, argmin ties, padded action tables, both pendulum loops) in the CPU suite; the GPU suite
+(tests/test_parity_gpu.py) runs the same comparisons on the device through the C ABI."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle
+from pyro_b200 import problem
+from tests.cases import CASES, build_case
+from tests.conftest import load_golden
+from tests.emu import emu
+
+
+def run_sweeps(P, J, k, lanes, generic=False):
+    pi = st = None
+    for _ in range(k):
+        J_prev = J
+        J, pi, st = emu.sweep(P, J_prev, lanes=lanes, force_generic=generic)
+        d = J - J_prev
+        assert st[0] == J.max() and st[1] == d.max() and st[2] == d.min()   # the fused dJ statistics
+    return J, pi
+
+
+@pytest.mark.parametrize("lanes", [1, 4, 16])
+@pytest.mark.parametrize("name", list(CASES))
+def test_emulated_kernels_match_reference_goldens(name, lanes):
+    case, gold = CASES[name], load_golden(name)
+    _, grid, cf = build_case(case)
+    P = problem.extract(grid, cf, case.get("alpha", 1.0))
+    k = case["snapshots"][0] if lanes == 16 else case["snapshots"][1]
+    k = min(k, 5)
+    J, pi = run_sweeps(P, gold["J0"], k, lanes)
+    if f"J_{k}" in gold:
+        assert np.array_equal(J, gold[f"J_{k}"]) and np.array_equal(pi, gold[f"pi_{k}"])
+    else:   # no snapshot at this sweep count: the C oracle (itself pinned by the fixtures) is the comparison
+        Jr, pr, _ = c_oracle.run(P, k)
+        assert np.array_equal(J, Jr) and np.array_equal(pi, pr)
+
+
+@pytest.mark.parametrize("lanes", [1, 4])
+@pytest.mark.parametrize("name", ["pend_51x51x11", "pend_time_41x61x7"])
+def test_emulated_order_agnostic_pendulum_loop(name, lanes):
+    case, gold = CASES[name], load_golden(name)
+    _, grid, cf = build_case(case)
+    P = problem.extract(grid, cf, case.get("alpha", 1.0))
+    k = case["snapshots"][0]
+    J, pi = run_sweeps(P, gold["J0"], k, lanes, generic=True)
+    assert np.array_equal(J, gold[f"J_{k}"]) and np.array_equal(pi, gold[f"pi_{k}"])
+
+
+@pytest.mark.parametrize("order", ["descending", "shuffled"])
+def test_emulated_pendulum_with_permuted_action_tables(order):
+    """Not ascending B.u: the library (and the emulator's copy of its selection rule) must take the generic loop."""
+    case = dict(system="SinglePendulum", x_grid_dim=[33, 41], u_grid_dim=[13], xbar=[-3.14, 0.0], INF=300.0,
+                u_lb=[-8.0], u_ub=[8.0], sys_params={"d1": 0.2})
+    _, grid, cf = build_case(case)
+    P = problem.extract(grid, cf, 1.0)
+    perm = np.arange(P.A)[::-1] if order == "descending" else np.random.default_rng(11).permutation(P.A)
+    P.tables["bu"][:] = P.tables["bu"][perm]
+    P.tables["gu"][:] = P.tables["gu"][perm]
+    J0 = np.random.default_rng(5).uniform(0, 300, P.N)
+    J, pi, _ = emu.sweep(P, J0, lanes=1)
+    Jr, pr = c_oracle.sweep_fused(P, J0)
+    assert np.array_equal(J, Jr) and np.array_equal(pi, pr)
+
+
+@pytest.mark.parametrize("name,case", [
+    ("pend_129", dict(system="SinglePendulum", x_grid_dim=[37, 150], u_grid_dim=[41], xbar=[-3.14, 0.0], INF=300.0)),
+    ("cartpole_mid", dict(CASES["cartpole_swingup"], x_grid_dim=[7, 9, 13, 17], u_grid_dim=[11])),
+    ("twolink_mid", dict(CASES["twolink_soft"], x_grid_dim=[7, 6, 12, 15], u_grid_dim=[5, 7])),
+    ("dpend_mid", dict(CASES["dpend_example"], x_grid_dim=[6, 7, 15, 12], u_grid_dim=[7, 5])),
+])
+def test_emulated_kernels_on_rough_J_equal_c_oracle(name, case):
+    """Random J (every corner weight matters), rows longer than a block, a ragged last chunk; lanes = 1 and 4."""
+    _, grid, cf = build_case(case)
+    P = problem.extract(grid, cf, case.get("alpha", 1.0))
+    J0 = np.random.default_rng(0).uniform(0, 300, P.N)
+    Jr, pr = c_oracle.sweep_fused(P, J0)
+    for lanes in (1, 4):
+        J, pi, _ = emu.sweep(P, J0, lanes=lanes)
+        assert np.array_equal(J, Jr) and np.array_equal(pi, pr), lanes
