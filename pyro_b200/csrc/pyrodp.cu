@@ -27,207 +27,7 @@
 
 #include "sweep_fused.cuh"
 
-// ---- LUT mode: generic n in {2,3,4}, tables in HBM (dynamicprogramming.py:557-570) ---------------
-// A group of G lanes owns one node and strides over its actions, so the x_next / G rows are read
-// with contiguous, vectorisable accesses; the min/argmin over actions is a warp-shuffle reduction
-// with lowest-index tie break (np.argmin).
-template <int N>
-__device__ __forceinline__ double rgi_linear(const DevProblem& P, const double* __restrict__ Jn, const double* x, bool& oob) {
-    int c[N];
-    double y[N];
-    oob = false;
-#pragma unroll
-    for (int d = 0; d < N; ++d) oob = oob || (x[d] < P.lb[d]) || (x[d] > P.ub[d]);
-    if (oob) return 0.0;  // fill_value (_rgi.py:476-477)
-#pragma unroll
-    for (int d = 0; d < N; ++d) {
-        // scipy's find_interval_ascending: arithmetic guess, then the level table decides
-        const double* __restrict__ lev = P.level[d];
-        const int nlev = P.dims[d];
-        int k = min(max((int)((x[d] - P.lb[d]) * P.inv_step[d]), 0), nlev - 2);
-        double lo = __ldg(lev + k), hi = __ldg(lev + k + 1);
-        while (x[d] < lo && k > 0) { --k; hi = lo; lo = __ldg(lev + k); }
-        while (x[d] >= hi && k < nlev - 2) { ++k; lo = hi; hi = __ldg(lev + k + 1); }
-        c[d] = k;
-        y[d] = exact_div(x[d] - lo, hi - lo, __ldg(P.rinv[d] + k));   // correctly rounded quotient, 3 FP64 issues
-    }
-    if (N == 2) {
-        const double* p = Jn + (long long)c[0] * P.dims[1] + c[1];
-        const double v00 = __ldg(p), v01 = __ldg(p + 1), v10 = __ldg(p + P.dims[1]), v11 = __ldg(p + P.dims[1] + 1);
-        double r = v00 * (1.0 - y[0]) * (1.0 - y[1]);
-        r = r + v01 * (1.0 - y[0]) * y[1];
-        r = r + v10 * y[0] * (1.0 - y[1]);
-        r = r + v11 * y[0] * y[1];
-        return r;
-    }
-    long long off = 0;
-#pragma unroll
-    for (int d = 0; d < N; ++d) off += (long long)c[d] * P.stride[d];
-    double value = 0.0;
-#pragma unroll
-    for (int corner = 0; corner < (1 << N); ++corner) {
-        double w = 1.0;
-        long long o = off;
-#pragma unroll
-        for (int d = 0; d < N; ++d) {
-            const int bit = (corner >> (N - 1 - d)) & 1;  // axis 0 slowest (itertools.product order)
-            w = w * (bit ? y[d] : (1.0 - y[d]));
-            o += bit ? P.stride[d] : 0;
-        }
-        value = value + __ldg(Jn + o) * w;
-    }
-    return value;
-}
-
-template <int N, int G>
-__global__ void __launch_bounds__(SWEEP_THREADS)
-sweep_lut_kernel(const __grid_constant__ DevProblem P, const double* __restrict__ Jn, double* __restrict__ Jo,
-                 long long* __restrict__ pi, const double* __restrict__ xnext, const double* __restrict__ Gtab,
-                 unsigned long long* __restrict__ partials, unsigned int* counter, double* __restrict__ stats) {
-    // Persistent grid: one resident wave of blocks strides over the nodes, so the statistics epilogue (three
-    // atomics and one ticket per BLOCK) stays negligible however many nodes there are — with one block per 128
-    // nodes the ticket counter alone serialised a 16M-node policy-evaluation sweep (r01B).
-    const int lane_in_group = threadIdx.x % G;
-    const int A = P.A;
-    const long long total = P.node_end - P.node_begin;
-    const long long gstride = (long long)gridDim.x * blockDim.x / G;
-    const long long iters = (total + gstride - 1) / gstride;   // the same trip count for every thread: shuffles inside
-    Stats3 st = stats_identity();
-    for (long long it = 0; it < iters; ++it) {
-        const long long node = P.node_begin + it * gstride + ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
-        const long long slot = node - P.slab_node_begin;  // row of the (slab-local) x_next / G tables
-        const bool active = node < P.node_end;
-        double best = __longlong_as_double(0x7ff0000000000000LL);
-        int besta = 0x7fffffff;
-        if (active) {
-            const double* __restrict__ xrow = xnext + slot * (long long)A * N;
-            const double* __restrict__ grow = Gtab + slot * (long long)A;
-            for (int a = lane_in_group; a < A; a += G) {
-                double x[N];
-#pragma unroll
-                for (int d = 0; d < N; ++d) x[d] = __ldcs(xrow + (long long)a * N + d);
-                bool oob;
-                const double Jx = rgi_linear<N>(P, Jn, x, oob);
-                const double Qa = __ldcs(grow + a) + P.alpha * Jx;
-                if (Qa < best) { best = Qa; besta = a; }
-            }
-        }
-        lane_group_argmin(best, besta, G);
-        if (active && lane_in_group == 0) {
-            if (besta == 0x7fffffff) besta = 0;  // no Q below +inf: np.argmin of a constant row is 0
-            Jo[node] = best;
-            pi[node] = besta;
-            const double d = best - Jn[node];
-            Stats3 mine;
-            mine.jmax = best; mine.dmax = d; mine.dmin = d;
-            stats_merge(st, mine);
-        }
-    }
-    block_stats_finish(st, partials, counter, stats);
-}
-
-// ---- policy evaluation: LUT mode with ONE table column per node (dynamicprogramming.py:743-752) --------
-// J = G + alpha * RGI(J_next)(x_next_table): no min, 8n + 32 bytes of HBM traffic per node and a few dozen
-// instructions — the streaming member of the family.  A persistent grid strides over the nodes; each thread
-// takes U nodes per trip (a grid-strided tile, so every access of a warp is contiguous) and issues all their
-// table loads before the first interpolation.  Measured (r01E, 4001^2 nodes): U = 1 at 32 registers and full
-// occupancy wins — 0.162 ms, 4.74 TB/s of algorithmic traffic = 72 % of the measured HBM copy peak — over
-// U = 2 (0.181), 4 (0.213), 8 (0.293).
-#ifndef POLICY_U2
-#define POLICY_U2 1   // nodes per thread and trip, n = 2: occupancy beats per-thread memory parallelism (profiles/r01E_policy_variants.txt)
-#endif
-#ifndef POLICY_U4
-#define POLICY_U4 1   // the same, n = 3 and 4
-#endif
-template <int N, int U>
-__global__ void __launch_bounds__(256)
-sweep_policy_kernel(const __grid_constant__ DevProblem P, const double* __restrict__ Jn, double* __restrict__ Jo,
-                    long long* __restrict__ pi, const double* __restrict__ xnext, const double* __restrict__ Gtab,
-                    unsigned long long* __restrict__ partials, unsigned int* counter, double* __restrict__ stats) {
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long tstride = (long long)gridDim.x * blockDim.x;
-    Stats3 st = stats_identity();
-    for (long long first = P.node_begin; first < P.node_end; first += tstride * U) {
-        double x[U][N], g[U], jn[U];
-        bool act[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long node = first + u * tstride + tid;
-            act[u] = node < P.node_end;
-            if (act[u]) {
-                const long long slot = node - P.slab_node_begin;   // row of the (slab-local) tables
-                const double2* __restrict__ xr = (const double2*)(xnext + slot * N);   // N even: 16-byte aligned rows
-                if (N % 2 == 0) {
-#pragma unroll
-                    for (int d = 0; d < N; d += 2) {
-                        const double2 v = __ldcs(xr + d / 2);
-                        x[u][d] = v.x; x[u][d + 1] = v.y;
-                    }
-                } else {
-#pragma unroll
-                    for (int d = 0; d < N; ++d) x[u][d] = __ldcs(xnext + slot * N + d);
-                }
-                g[u] = __ldcs(Gtab + slot);
-                jn[u] = __ldg(Jn + node);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (act[u]) {
-                const long long node = first + u * tstride + tid;
-                bool oob;
-                const double Jx = rgi_linear<N>(P, Jn, x[u], oob);
-                const double Q = g[u] + P.alpha * Jx;
-                Jo[node] = Q;
-                pi[node] = 0;
-                const double d = Q - jn[u];
-                Stats3 mine;
-                mine.jmax = Q; mine.dmax = d; mine.dmin = d;
-                stats_merge(st, mine);
-            }
-        }
-    }
-    block_stats_finish(st, partials, counter, stats);
-}
-
-// ---- terminal cost (dynamicprogramming.py:159-171) -------------------------------------------------
-template <int N>
-__global__ void terminal_cost_kernel(const __grid_constant__ DevProblem P, double* __restrict__ J, long long* __restrict__ pi,
-                                     long long first, long long last) {
-    // J and pi are virtual bases indexed by global node id; [first,last) = allocated planes (slab + halo)
-    const long long node = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (node >= last) return;
-    double dx[N];
-    long long r = node;
-#pragma unroll
-    for (int d = N - 1; d >= 0; --d) {
-        const int i = (int)(r % P.dims[d]);
-        r /= P.dims[d];
-        dx[d] = __ldg(P.level[d] + i) - P.xbar[d];
-    }
-    double h = 0.0;
-    if (P.cost_id == PDP_COST_QUADRATIC) {
-        h = quad_form<N>(P.S, dx);
-        if (P.ontarget_check && norm2<N>(dx) < P.EPS) h = 0.0;
-    }
-    J[node] = h;
-    if (node >= P.node_begin && node < P.node_end) pi[node] = 0;
-}
-
-// ---- after the sweep: pi -> u_k table (discretizer.py:616-633), infeasible-set cleaning (:322-334) ----
-__global__ void input_from_policy_kernel(const long long* __restrict__ pi, const double* __restrict__ u_flat, int m, int k,
-                                         double* __restrict__ out, long long n) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = __ldg(u_flat + pi[i] * m + k);
-}
-__global__ void clean_infeasible_kernel(double* __restrict__ J, long long* __restrict__ pi, double thr, double INF,
-                                        long long def_action, long long n) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && J[i] > thr) {
-        J[i] = INF;
-        pi[i] = def_action;
-    }
-}
+#include "table_kernels.cuh"
 
 // exposed for tests: exact_div against IEEE division on the device
 __global__ void exact_div_test_kernel(const double* a, const double* den, double* q_fast, double* q_ieee, long long n) {

@@ -6,6 +6,7 @@ mkdir -p "$HERE/gen"
 # the only source rewrite: "extern __shared__ <type> name[]" (dynamic shared memory) becomes a plain extern of the emulator's array
 sed -e 's/extern __shared__/extern/' "$ROOT/pyro_b200/csrc/pyrodp_device.cuh" > "$HERE/gen/pyrodp_device.cuh"
 sed -e 's/extern __shared__/extern/' "$ROOT/pyro_b200/csrc/sweep_fused.cuh" > "$HERE/gen/sweep_fused.cuh"
+sed -e 's/extern __shared__/extern/' "$ROOT/pyro_b200/csrc/table_kernels.cuh" > "$HERE/gen/table_kernels.cuh"
 # -ffp-contract=off: like nvcc -fmad=false, a*b+c is never fused unless the source says fma()
 g++ -std=c++17 -O1 -g -ffp-contract=off -fno-fast-math -fPIC -shared -Wno-unused-variable \
     -o "$HERE/libpyrodp_emu.so" "$HERE/emu_main.cpp"

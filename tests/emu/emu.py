@@ -16,12 +16,16 @@ def load():
     if _lib is None:
         srcs = [os.path.join(HERE, f) for f in ("emu_main.cpp", "cuda_emu.h", "build.sh")]
         root = os.path.dirname(os.path.dirname(HERE))
-        srcs += [os.path.join(root, "pyro_b200", "csrc", f) for f in ("pyrodp_device.cuh", "sweep_fused.cuh")]
+        srcs += [os.path.join(root, "pyro_b200", "csrc", f) for f in ("pyrodp_device.cuh", "sweep_fused.cuh", "table_kernels.cuh")]
         if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
             subprocess.check_call(["bash", os.path.join(HERE, "build.sh")])
         _lib = C.CDLL(LIB)
         _lib.emu_sweep.restype = C.c_int
         _lib.emu_sweep.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        _lib.emu_lut_sweep.restype = C.c_int
+        _lib.emu_lut_sweep.argtypes = [C.c_void_p] * 7 + [C.c_int]
+        _lib.emu_terminal.restype = C.c_int
+        _lib.emu_terminal.argtypes = [C.c_void_p] * 3
     return _lib
 
 
@@ -36,3 +40,28 @@ def sweep(problem, J_next, lanes=1, force_generic=False):
     if rc != 0:
         raise RuntimeError(f"emu_sweep failed ({rc})")
     return J, pi, stats
+
+
+def lut_sweep(problem, J_next, x_next, G, grid_blocks=24):
+    """One LUT-mode backup (generic kernel, or the policy-evaluation kernel when the tables have one column) on a
+    persistent grid of `grid_blocks` blocks: (J, pi, stats)."""
+    J_next = np.ascontiguousarray(J_next, dtype=np.float64)
+    x_next = np.ascontiguousarray(x_next, dtype=np.float64)
+    G = np.ascontiguousarray(G, dtype=np.float64)
+    J = np.empty(problem.N)
+    pi = np.empty(problem.N, dtype=np.int64)
+    stats = np.empty(3)
+    rc = load().emu_lut_sweep(C.addressof(problem.c), J_next.ctypes.data, x_next.ctypes.data, G.ctypes.data, J.ctypes.data,
+                              pi.ctypes.data, stats.ctypes.data, int(grid_blocks))
+    if rc != 0:
+        raise RuntimeError(f"emu_lut_sweep failed ({rc})")
+    return J, pi, stats
+
+
+def terminal(problem):
+    J = np.empty(problem.N)
+    pi = np.full(problem.N, -1, dtype=np.int64)
+    rc = load().emu_terminal(C.addressof(problem.c), J.ctypes.data, pi.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"emu_terminal failed ({rc})")
+    return J, pi

@@ -125,6 +125,7 @@ void emu_launch(emu_uint3 grid, emu_uint3 block, const std::function<void()>& bo
 
 #include "gen/pyrodp_device.cuh"
 #include "gen/sweep_fused.cuh"
+#include "gen/table_kernels.cuh"
 
 typedef void (*fused_kernel_t)(const DevProblem, const double*, double*, long long*, unsigned long long*, unsigned int*, double*);
 
@@ -178,6 +179,7 @@ static void fill(const pdp_problem* p, HostProblem& H) {
     for (int t = 0; t < 4; ++t)
         if (p->sys_tab[t] && p->sys_tab_len[t] > 0) P.tab[t] = H.hold(p->sys_tab[t], (size_t)p->sys_tab_len[t]);
     P.all_act_ok = 1;
+    if (p->system_id == PDP_SYS_LUT) return;
     std::vector<double> bu(p->bu, p->bu + (size_t)A * P.dof);
     for (long long a = 0; a < A; ++a)
         if (!p->act_ok[a]) {
@@ -217,6 +219,63 @@ extern "C" int emu_sweep(const pdp_problem* p, const double* J_next, double* J, 
         std::vector<unsigned long long> slots(3 * STATS_SLOTS, 0);
         unsigned int counter = 0;
         emu_launch(grid, block, [&]() { k(P, J_next, J, pi, slots.data(), &counter, stats3); });
+        return 0;
+    } catch (const std::exception&) {
+        return -3;
+    }
+}
+
+// LUT mode (dynamicprogramming.py:557-570) and its one-column special case, policy evaluation (:743-752), launched
+// as pyrodp.cu launches them: the streaming kernel when A == 1, else the generic kernel with G = min(32, 2^ceil(log2 A)).
+extern "C" int emu_lut_sweep(const pdp_problem* p, const double* J_next, const double* x_next, const double* Gtab, double* J,
+                             long long* pi, double* stats3, int grid_blocks) {
+    if (!p) return -1;
+    try {
+        HostProblem H;
+        fill(p, H);
+        DevProblem& P = H.P;
+        std::vector<unsigned long long> slots(3 * STATS_SLOTS, 0);
+        unsigned int counter = 0;
+        const long long nodes = P.N;
+        if (P.A == 1) {
+            const long long blocks = std::min<long long>((nodes + 255) / 256, grid_blocks);
+            emu_uint3 grid = {(unsigned)blocks, 1, 1}, block = {256, 1, 1};
+            emu_launch(grid, block, [&]() {
+                if (P.n == 2) sweep_policy_kernel<2, POLICY_U2>(P, J_next, J, pi, x_next, Gtab, slots.data(), &counter, stats3);
+                else if (P.n == 3) sweep_policy_kernel<3, POLICY_U4>(P, J_next, J, pi, x_next, Gtab, slots.data(), &counter, stats3);
+                else sweep_policy_kernel<4, POLICY_U4>(P, J_next, J, pi, x_next, Gtab, slots.data(), &counter, stats3);
+            });
+            return 0;
+        }
+        int G = 1;
+        while (G < 32 && G < P.A) G <<= 1;
+        const long long blocks = std::min<long long>((nodes * G + SWEEP_THREADS - 1) / SWEEP_THREADS, grid_blocks);
+        emu_uint3 grid = {(unsigned)blocks, 1, 1}, block = {SWEEP_THREADS, 1, 1};
+#define EMU_LUT(NN, GG) sweep_lut_kernel<NN, GG>(P, J_next, J, pi, x_next, Gtab, slots.data(), &counter, stats3)
+#define EMU_LUT_N(NN)                                                                                        \
+    switch (G) { case 1: EMU_LUT(NN, 1); break; case 2: EMU_LUT(NN, 2); break; case 4: EMU_LUT(NN, 4); break;  \
+                 case 8: EMU_LUT(NN, 8); break; case 16: EMU_LUT(NN, 16); break; default: EMU_LUT(NN, 32); }
+        emu_launch(grid, block, [&]() {
+            if (P.n == 2) { EMU_LUT_N(2) } else if (P.n == 3) { EMU_LUT_N(3) } else { EMU_LUT_N(4) }
+        });
+        return 0;
+    } catch (const std::exception&) {
+        return -3;
+    }
+}
+
+// evaluate_terminal_cost (dynamicprogramming.py:159-171)
+extern "C" int emu_terminal(const pdp_problem* p, double* J, long long* pi) {
+    if (!p || p->system_id == PDP_SYS_LUT) return -1;
+    try {
+        HostProblem H;
+        fill(p, H);
+        DevProblem& P = H.P;
+        emu_uint3 grid = {(unsigned)((P.N + 255) / 256), 1, 1}, block = {256, 1, 1};
+        emu_launch(grid, block, [&]() {
+            if (P.n == 2) terminal_cost_kernel<2>(P, J, pi, 0, P.N);
+            else terminal_cost_kernel<4>(P, J, pi, 0, P.N);
+        });
         return 0;
     } catch (const std::exception&) {
         return -3;

@@ -81,3 +81,81 @@ def test_emulated_kernels_on_rough_J_equal_c_oracle(name, case):
     for lanes in (1, 4):
         J, pi, _ = emu.sweep(P, J0, lanes=lanes)
         assert np.array_equal(J, Jr) and np.array_equal(pi, pr), lanes
+
+
+# ---- table-mode kernels (pyro_b200/csrc/table_kernels.cuh) ---------------------------------------------------------
+from oracle import np_oracle as npo  # noqa: E402
+from tests.cases import POLICY_CASES, oracle_objects  # noqa: E402
+
+
+@pytest.mark.parametrize("name", ["pend_51x51x11", "cartpole_swingup"])
+def test_emulated_lut_kernel_matches_reference_goldens(name):
+    """sweep_lut_kernel on reference-identical tables (dynamicprogramming.py:557-570), persistent grid."""
+    case, gold = CASES[name], load_golden(name)
+    _, grid, cf = build_case(case)
+    ogrid, ocost = oracle_objects(case)
+    x_next, _, _, G = ogrid.tables(ocost)
+    P = problem.extract(grid, cf, case.get("alpha", 1.0), force_lut=True)
+    J, k = gold["J0"], case["snapshots"][1]
+    for _ in range(k):
+        J, pi, _ = emu.lut_sweep(P, J, x_next, G)
+    assert np.array_equal(J, gold[f"J_{k}"]) and np.array_equal(pi, gold[f"pi_{k}"])
+
+
+@pytest.mark.parametrize("name", list(POLICY_CASES))
+def test_emulated_policy_kernel_matches_reference_goldens(name):
+    """sweep_policy_kernel on the reference's own policy-evaluation tables (dynamicprogramming.py:683-752)."""
+    case, gold = POLICY_CASES[name], load_golden(name)
+    _, grid, cf = build_case(case)
+    P = problem.extract(grid, cf, case.get("alpha", 1.0), lut_actions=1)
+    J, k = gold["J0"], 0
+    for target in case["snapshots"][:2]:
+        for _ in range(target - k):
+            J_prev = J
+            J, pi, st = emu.lut_sweep(P, J_prev, gold["x_next_table"][:, None, :], gold["G"][:, None], grid_blocks=7)
+            assert (pi == 0).all() and st[0] == J.max() and st[1] == (J - J_prev).max()
+        k = target
+        assert np.array_equal(J, gold[f"J_{k}"])
+
+
+def test_emulated_table_kernels_3d_and_ragged_grids():
+    """n = 3 through both table kernels, grids that do not divide the persistent stride."""
+    rng = np.random.default_rng(3)
+    dims, A = (9, 7, 8), 6
+    levels = [np.linspace(-1, 1, dims[0]), np.linspace(0, 3, dims[1]), np.linspace(-2, 5, dims[2])]
+    N = int(np.prod(dims))
+    X = np.stack([g.reshape(-1) for g in np.meshgrid(*levels, indexing="ij")], axis=1)
+    x_next = X[:, None, :] + rng.normal(0, 0.4, (N, A, 3))
+    x_next[::17, 0, :] = X[::17]
+    x_next[5::19, 1, 2] = 5.0
+    G = rng.uniform(0, 1, (N, A))
+    J0 = rng.uniform(0, 50, N)
+
+    class Sys3:
+        n, m = 3, 1
+        x_lb, x_ub = np.array([-1.0, 0.0, -2.0]), np.array([1.0, 3.0, 5.0])
+        u_lb, u_ub = np.array([-1.0]), np.array([1.0])
+
+    class Grid3:
+        sys, dt = Sys3(), 0.05
+        x_grid_dim, u_grid_dim = np.array(dims), np.array([A])
+        x_level, u_level = levels, [np.linspace(-1, 1, A)]
+
+    class Cost3:
+        INF = 77.0
+    J, pi, _ = emu.lut_sweep(problem.extract(Grid3(), Cost3(), 0.97), J0, x_next, G, grid_blocks=5)
+    J_ref, pi_ref = npo.lut_sweep(levels, dims, J0, x_next, G, 0.97, use_scipy=True)
+    assert np.array_equal(J, J_ref) and np.array_equal(pi, pi_ref)
+    J1, pi1, _ = emu.lut_sweep(problem.extract(Grid3(), Cost3(), 0.97, lut_actions=1), J0, x_next[:, 2:3, :], G[:, 2:3], grid_blocks=3)
+    J1_ref, _ = npo.lut_sweep(levels, dims, J0, x_next[:, 2:3, :], G[:, 2:3], 0.97, use_scipy=True)
+    assert np.array_equal(J1, J1_ref) and (pi1 == 0).all()
+
+
+@pytest.mark.parametrize("name", ["pend_time_41x61x7", "dpend_example"])
+def test_emulated_terminal_cost_kernel(name):
+    case = dict(CASES[name], S=[2.0, 0.3] if name.startswith("pend") else [2.0, 0.3, 0.0, 1.5], cost="quadratic")
+    case.pop("EPS", None)
+    _, grid, cf = build_case(case)
+    P = problem.extract(grid, cf, 1.0)
+    J, pi = emu.terminal(P)
+    assert np.array_equal(J, c_oracle.terminal(P)) and (pi == 0).all()
