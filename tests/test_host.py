@@ -265,3 +265,32 @@ def test_grid_mirror_host_methods_equal_the_real_reference(name, tmp_path):
         p = np.array([[0.3, -0.2], [1.1, 0.7]])
         assert np.array_equal(grid.compute_bivariatespline_2D_interpolation_function(J).ev(p[:, 0], p[:, 1]),
                               rgrid.compute_bivariatespline_2D_interpolation_function(J).ev(p[:, 0], p[:, 1]))
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference not present (GPU box)")
+def test_controller_and_infeasible_cleaning_equal_the_real_reference():
+    """The step after the sweep (dynamicprogramming.py:27-107, 322-334, 472-477) on the mirror vs the unmodified
+    reference: same policy in -> same control law out, same J / pi after clean_infeasible_set."""
+    import importlib
+    gen = importlib.import_module("oracle.gen_golden")
+    ns = ref_loader.load()
+    case = dict(CASES["cartpole_swingup"], x_grid_dim=[5, 7, 5, 7])
+    with ref_loader.quiet():
+        rsys, rgrid, rcf, rdp = gen.build_reference(ns, case)
+        rdp.compute_steps(6)
+        rctl = rdp.get_lookup_table_controller()
+    _, grid, cf = build_case(case)
+    dp = dynamicprogramming.DynamicProgrammingWithLookUpTable(grid, cf, engine_factory=fake_factory)
+    dp.verbose = False
+    dp.compute_steps(6)
+    assert np.array_equal(dp.J, rdp.J) and np.array_equal(dp.pi, rdp.pi)
+    ctl = dp.get_lookup_table_controller()
+    rng = np.random.default_rng(8)
+    for _ in range(40):
+        x = rng.uniform(rsys.x_lb - 0.5, rsys.x_ub + 0.5)     # some states outside the grid: fill value 0
+        assert np.array_equal(ctl.c(x, ctl.rbar), rctl.c(x, rctl.rbar))
+        assert np.array_equal(ctl.cbar(x), rctl.cbar(x))
+    with ref_loader.quiet():
+        rdp.clean_infeasible_set(tol=1)
+    dp.clean_infeasible_set(tol=1)
+    assert np.array_equal(dp.J, rdp.J) and np.array_equal(dp.pi, rdp.pi)
