@@ -91,6 +91,12 @@ def main_policy():
                 pe.compute_steps(target - k)
                 k = target
                 out[f"J_{k}"] = pe.J.copy()
+            # the base class (per-node Python loop, :636-672): exact INF wherever the input is disallowed
+            pb = ns.dynamicprogramming.PolicyEvaluator(ctl, grid, cf)
+            pb.alpha = case.get("alpha", 1.0)
+            kb = case["snapshots"][1]
+            pb.compute_steps(kb)
+            out[f"Jbase_{kb}"] = pb.J.copy()
         path = os.path.join(OUT, name + ".npz")
         np.savez_compressed(path, **out)
         print(f"{name}: N={grid.nodes_n} snapshots={case['snapshots']} J_max={pe.J.max():.6f} "

@@ -295,21 +295,31 @@ class PolicyEvaluator(DynamicProgramming):
         eng.set_lut(self.x_next_table, self.G)
         return eng
 
+    # Base class semantics (dynamicprogramming.py:636-672): a node whose input OR arrival state is not allowed gets
+    # exactly INF.  The table variant (:700-752) instead computes INF + alpha*J(x_next) when only the input is
+    # disallowed and x_next lies inside the grid.  Both are reproduced: here such a node's table entry is moved
+    # outside the box, where the interpolation returns its fill value 0.
+    _invalid_input_is_exact_inf = True
+
     def compute_lookuptable(self):
         """x_next_table (N, n) and G (N,) of the control law (dynamicprogramming.py:683-729)."""
         gs, sys, cf = self.grid_sys, self.sys, self.cf
         X = gs.state_from_node_id
         self.x_next_table = np.zeros((gs.nodes_n, sys.n), dtype=float)
         self.G = np.zeros(gs.nodes_n, dtype=float)
+        outside = np.asarray(sys.x_ub, dtype=float) + 1.0
         for s in range(gs.nodes_n):
             x = X[s, :]
             u = self.ctl.c(x, self.ctl.rbar, self.t)
             x_next = sys.f(x, u, self.t) * gs.dt + x
             self.x_next_table[s, :] = x_next
-            if sys.isavalidinput(x, u) and sys.isavalidstate(x_next):
+            u_ok = sys.isavalidinput(x, u)
+            if u_ok and sys.isavalidstate(x_next):
                 self.G[s] = cf.g(x, u, self.t) * gs.dt
             else:
                 self.G[s] = cf.INF
+                if not u_ok and self._invalid_input_is_exact_inf:
+                    self.x_next_table[s, :] = outside
 
     def get_lookup_table_controller(self):
         raise NotImplementedError("a policy evaluation has no policy table; the controller is self.ctl")
@@ -319,7 +329,9 @@ class PolicyEvaluator(DynamicProgramming):
 
 
 class PolicyEvaluatorWithLookUpTable(PolicyEvaluator):
-    """Name kept for drop-in use (dynamicprogramming.py:677); the look-up tables are always used."""
+    """The table variant (dynamicprogramming.py:677-752), with the reference's own tables and its INF + alpha*J
+    value on nodes whose input alone is disallowed."""
+    _invalid_input_is_exact_inf = False
 
 
 def build_lookup_tables(grid_sys, cf, t=0):

@@ -159,3 +159,31 @@ def test_emulated_terminal_cost_kernel(name):
     P = problem.extract(grid, cf, 1.0)
     J, pi = emu.terminal(P)
     assert np.array_equal(J, c_oracle.terminal(P)) and (pi == 0).all()
+
+
+@pytest.mark.parametrize("name", list(POLICY_CASES))
+def test_emulated_base_class_policy_evaluator_semantics(name):
+    """PolicyEvaluator (the per-node base class, dynamicprogramming.py:636-672) gives exactly INF where the input is
+    disallowed, PolicyEvaluatorWithLookUpTable (:700-752) gives INF + alpha*J(x_next) there: the mirror builds the
+    tables for either, the policy kernel reproduces both reference classes."""
+    from pyro_b200 import dynamicprogramming as dpm
+    from tests.cases import LinearFeedback
+    case, gold = POLICY_CASES[name], load_golden(name)
+    _, grid, cf = build_case(case)
+
+    class NoEngine:
+        def __init__(self, N):
+            self.N, self.problem = N, type("P", (), {"system_id": 0})()
+        def set_J(self, J): pass
+        def get_J(self): return np.zeros(self.N)
+        def close(self): pass
+    kb = case["snapshots"][1]
+    for cls, key in ((dpm.PolicyEvaluator, f"Jbase_{kb}"), (dpm.PolicyEvaluatorWithLookUpTable, f"J_{kb}")):
+        pe = cls(LinearFeedback(**case["ctl"]), grid, cf, engine_factory=lambda dp, P: NoEngine(grid.nodes_n))
+        pe.compute_lookuptable()
+        P = problem.extract(grid, cf, case.get("alpha", 1.0), lut_actions=1)
+        J = gold["J0"]
+        for _ in range(kb):
+            J, _, _ = emu.lut_sweep(P, J, pe.x_next_table[:, None, :], pe.G[:, None], grid_blocks=5)
+        assert np.array_equal(J, gold[key]), cls.__name__
+    assert not np.array_equal(gold[f"Jbase_{kb}"], gold[f"J_{kb}"])   # the two reference classes really differ here

@@ -424,3 +424,9 @@ def test_policy_evaluation_matches_reference_goldens(name):
         k = target
         assert np.array_equal(pe.J, gold[f"J_{k}"]) and (pe.pi == 0).all()
     assert np.array_equal(pe.x_next_table, gold["x_next_table"]) and np.array_equal(pe.G, gold["G"])
+    # the per-node base class (dynamicprogramming.py:636-672): exactly INF wherever the input is disallowed
+    kb = case["snapshots"][1]
+    pb = dynamicprogramming.PolicyEvaluator(LinearFeedback(**case["ctl"]), grid, cf)
+    pb.alpha, pb.verbose = case.get("alpha", 1.0), False
+    pb.compute_steps(kb)
+    assert np.array_equal(pb.J, gold[f"Jbase_{kb}"])
