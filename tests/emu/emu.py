@@ -22,6 +22,8 @@ def load():
         _lib = C.CDLL(LIB)
         _lib.emu_sweep.restype = C.c_int
         _lib.emu_sweep.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        _lib.emu_sweep_planes.restype = C.c_int
+        _lib.emu_sweep_planes.argtypes = [C.c_void_p] * 5 + [C.c_int] * 4
         _lib.emu_lut_sweep.restype = C.c_int
         _lib.emu_lut_sweep.argtypes = [C.c_void_p] * 7 + [C.c_int]
         _lib.emu_terminal.restype = C.c_int
@@ -65,3 +67,15 @@ def terminal(problem):
     if rc != 0:
         raise RuntimeError(f"emu_terminal failed ({rc})")
     return J, pi
+
+
+def sweep_planes(problem, J_next, J, pi, p0, p1, lanes=1, force_generic=False):
+    """Backup of axis-0 planes [p0, p1) only, written into the full-size arrays J / pi: what one rank (or one
+    boundary / interior launch of it) computes.  Returns the statistics triple of those planes."""
+    assert J_next.dtype == np.float64 and J.dtype == np.float64 and pi.dtype == np.int64
+    stats = np.empty(3)
+    rc = load().emu_sweep_planes(C.addressof(problem.c), J_next.ctypes.data, J.ctypes.data, pi.ctypes.data, stats.ctypes.data,
+                                 int(lanes), int(bool(force_generic)), int(p0), int(p1))
+    if rc != 0:
+        raise RuntimeError(f"emu_sweep_planes failed ({rc})")
+    return stats

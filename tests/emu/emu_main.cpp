@@ -195,8 +195,10 @@ static void fill(const pdp_problem* p, HostProblem& H) {
     P.gu = H.hold(p->gu, (size_t)A);
 }
 
-extern "C" int emu_sweep(const pdp_problem* p, const double* J_next, double* J, long long* pi, double* stats3, int lanes,
-                         int force_generic) {
+// One backup of axis-0 planes [p0, p1) — the launch pyrodp.cu's launch_planes() makes for a rank's slab (or for a
+// boundary / interior sub-range of it).  J_next, J and pi are indexed by the global node id.
+extern "C" int emu_sweep_planes(const pdp_problem* p, const double* J_next, double* J, long long* pi, double* stats3, int lanes,
+                                int force_generic, int p0, int p1) {
     if (!p || p->system_id == PDP_SYS_LUT) return -1;
     try {
         HostProblem H;
@@ -209,13 +211,19 @@ extern "C" int emu_sweep(const pdp_problem* p, const double* J_next, double* J, 
         if (G == 1) k = a1 ? fused_for<1, true>(P.system_id, nd, mono) : fused_for<1, false>(P.system_id, nd, mono);
         else if (G == 4) k = a1 ? fused_for<4, true>(P.system_id, nd, mono) : fused_for<4, false>(P.system_id, nd, mono);
         else if (G == 16) k = a1 ? fused_for<16, true>(P.system_id, nd, mono) : fused_for<16, false>(P.system_id, nd, mono);
-        if (!k) return -2;
+        if (!k || p0 < 0 || p1 > P.dims[0] || p0 >= p1) return -2;
+        const long long plane = P.N / P.dims[0];
+        P.node_begin = (long long)p0 * plane;
+        P.node_end = (long long)p1 * plane;
         emu_uint3 grid, block = {SWEEP_THREADS, 1, 1};
-        if (P.system_id == PDP_SYS_PENDULUM)
-            grid = {(unsigned)P.dims[0], (unsigned)(((long long)P.dims[1] * G + SWEEP_THREADS - 1) / SWEEP_THREADS), 1};
-        else
-            grid = {(unsigned)(P.dims[0] * P.dims[1]),
+        if (P.system_id == PDP_SYS_PENDULUM) {
+            P.plane_begin = p0;
+            grid = {(unsigned)(p1 - p0), (unsigned)(((long long)P.dims[1] * G + SWEEP_THREADS - 1) / SWEEP_THREADS), 1};
+        } else {
+            P.plane_begin = (long long)p0 * P.dims[1];
+            grid = {(unsigned)((p1 - p0) * P.dims[1]),
                     (unsigned)(((long long)P.dims[2] * P.dims[3] * G + SWEEP_THREADS - 1) / SWEEP_THREADS), 1};
+        }
         std::vector<unsigned long long> slots(3 * STATS_SLOTS, 0);
         unsigned int counter = 0;
         emu_launch(grid, block, [&]() { k(P, J_next, J, pi, slots.data(), &counter, stats3); });
@@ -223,6 +231,11 @@ extern "C" int emu_sweep(const pdp_problem* p, const double* J_next, double* J, 
     } catch (const std::exception&) {
         return -3;
     }
+}
+
+extern "C" int emu_sweep(const pdp_problem* p, const double* J_next, double* J, long long* pi, double* stats3, int lanes,
+                         int force_generic) {
+    return p ? emu_sweep_planes(p, J_next, J, pi, stats3, lanes, force_generic, 0, p->dims[0]) : -1;
 }
 
 // LUT mode (dynamicprogramming.py:557-570) and its one-column special case, policy evaluation (:743-752), launched

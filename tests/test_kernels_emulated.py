@@ -187,3 +187,38 @@ def test_emulated_base_class_policy_evaluator_semantics(name):
             J, _, _ = emu.lut_sweep(P, J, pe.x_next_table[:, None, :], pe.G[:, None], grid_blocks=5)
         assert np.array_equal(J, gold[key]), cls.__name__
     assert not np.array_equal(gold[f"Jbase_{kb}"], gold[f"J_{kb}"])   # the two reference classes really differ here
+
+
+@pytest.mark.parametrize("name,world", [("pend_101x101x21", 4), ("pend_time_41x61x7", 3), ("cartpole_swingup", 3),
+                                        ("dpend_example", 2), ("twolink_soft", 3)])
+def test_emulated_slab_sweeps_need_only_their_halo(name, world):
+    """The multi-GPU data path on the CPU: every rank's launch (the plane ranges pyrodp.cu issues, boundary planes
+    first) sees J_next ONLY on its slab + the halo pdp_compute_halo promises — everything else is NaN — and the
+    assembled result must equal the whole-grid backup bit for bit, statistics included."""
+    import ctypes as C
+    from pyro_b200 import _lib, distributed
+    case = CASES[name]
+    _, grid, cf = build_case(case)
+    P = problem.extract(grid, cf, case.get("alpha", 1.0))
+    lo, hi = C.c_int32(), C.c_int32()
+    _lib.check(_lib.load().pdp_compute_halo(C.byref(P.c), C.byref(lo), C.byref(hi)))
+    lo, hi = lo.value, hi.value
+    n0 = P.dims[0]
+    plane = P.N // n0
+    J0 = np.random.default_rng(1).uniform(0, 200, P.N)
+    J_ref, pi_ref, st_ref = emu.sweep(P, J0, lanes=1)
+    J = np.full(P.N, -1.0)
+    pi = np.full(P.N, -1, dtype=np.int64)
+    stats = []
+    for r in range(world):
+        b, e = distributed.balanced_slab(r, world, n0)
+        seen = np.full(P.N, np.nan)                         # what this rank holds: its slab and its halo, nothing else
+        a0, a1 = max(0, b - lo), min(n0, e + hi)
+        seen[a0 * plane:a1 * plane] = J0[a0 * plane:a1 * plane]
+        ranges = [(b, e)] if e - b <= lo + hi else [(b, b + hi), (e - lo, e), (b + hi, e - lo)]   # boundary first, then interior
+        for p0, p1 in ranges:
+            if p1 > p0:
+                stats.append(emu.sweep_planes(P, seen, J, pi, p0, p1, lanes=1))
+    assert np.array_equal(J, J_ref) and np.array_equal(pi, pi_ref)
+    stats = np.array(stats)
+    assert stats[:, 0].max() == st_ref[0] and stats[:, 1].max() == st_ref[1] and stats[:, 2].min() == st_ref[2]
