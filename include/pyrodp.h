@@ -135,6 +135,10 @@ int pdp_set_J(pdp_handle* h, const double* J_host);
 int pdp_get_J(pdp_handle* h, double* J_host);       /* slab doubles  */
 int pdp_get_J_next(pdp_handle* h, double* J_host);  /* slab doubles  */
 int pdp_get_pi(pdp_handle* h, int64_t* pi_host);    /* slab int64    */
+/* `count` values starting at GLOBAL node id node_begin (inside the handle's slab) of J (which = 0), J_next (1;
+ * doubles) or pi (2; int64): J[s0:s1] / pi[s0:s1] of the reference's arrays without moving the whole grid —
+ * what sampled parity checks and look-ups on 10^9-node grids need */
+int pdp_get_range(pdp_handle* h, int32_t which, int64_t node_begin, int64_t count, void* out_host);
 
 /* ---- the hot path ---------------------------------------------------------------------------
  * replaces initialize_backward_step + compute_backward_step + the reductions of
@@ -216,6 +220,8 @@ int64_t pdp_nodes_padded(const pdp_handle* h); /* N_pad: allocation size of the 
 int64_t pdp_actions(const pdp_handle* h);      /* A = prod(udims) */
 /* number of sweep-kernel launches issued by this handle so far (bench.py gpu_launches) */
 int64_t pdp_launch_count(const pdp_handle* h);
+/* name of the sweep kernel this handle launches, e.g. "sweep_mech2_range_kernel<TWOLINK,direct> G=1" */
+int pdp_kernel_info(const pdp_handle* h, char* out, int32_t len);
 /* device time in ms of the last pdp_sweep() call, measured with CUDA events on the handle's stream */
 double pdp_last_sweep_ms(const pdp_handle* h);
 

@@ -52,6 +52,8 @@ SIGNATURES = {
     "pdp_get_J": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pdp_get_J_next": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pdp_get_pi": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pdp_get_range": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p]),
+    "pdp_kernel_info": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32]),
     "pdp_sweep": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "pdp_sweep_enqueue": (C.c_int, [C.c_void_p]),
     "pdp_sweep_collect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),

@@ -26,6 +26,8 @@
 // =================================================================================================
 
 #include "sweep_fused.cuh"
+#include "sweep_mech2.cuh"
+#include "mech2_plan.h"
 
 #include "table_kernels.cuh"
 
@@ -134,6 +136,10 @@ struct pdp_handle {
     int policy_blocks = 0;        // one resident wave of sweep_policy_kernel blocks
     bool pend_mono = false;       // pendulum: x_next[1] is non-decreasing along the action list (see sweep_fused.cuh, MONO)
     bool force_generic = false;   // test hook (PYRODP_GENERIC=1): use the order-agnostic action loop anyway
+    int mech2_mode = 0;           // 4-D fused systems: 0 order-agnostic kernel, 1 range kernel (direct cells), 2 range kernel (cached cell)
+    int force_mech2 = -1;         // test / A-B hook (PYRODP_MECH2=generic|direct|cache)
+    Mech2Plan plan{};             // action-table structure the range kernel relies on
+    std::vector<double> hinv_host;  // inv(H) table (4 per axis-1 level), kept for the cell-displacement estimate
     void* fused = nullptr;        // selected fused kernel instantiation
     // multi-GPU (one process per GPU): NCCL communicator, side stream for the halo exchange
     void* comm = nullptr;
@@ -268,9 +274,28 @@ static int select_fused_kernel(pdp_handle* h) {
     else if (G == 4) k = a1 ? fused_for<4, true>(P.system_id, nd, mono) : fused_for<4, false>(P.system_id, nd, mono);
     else k = a1 ? fused_for<16, true>(P.system_id, nd, mono) : fused_for<16, false>(P.system_id, nd, mono);
     if (!k) return fail(h, PDP_ENOTSUP, "no fused kernel for this system");
+    const size_t A = (size_t)P.A;
+    // 4-D systems, one lane per node: the range-skipping kernel when the action table has the structure it relies on
+    h->mech2_mode = 0;
+    if (P.system_id != PDP_SYS_PENDULUM && G == 1 && h->plan.ok && !h->force_generic && h->force_mech2 != 0) {
+        const double cell2 = (P.ub[2] - P.lb[2]) / (P.dims[2] - 1), cell3 = (P.ub[3] - P.lb[3]) / (P.dims[3] - 1);
+        const double cells = mech2_cells_per_action(h->plan, h->hinv_host.data(), P.dims[1], P.dt, cell2, cell3);
+        int mode = cells < 0.7 ? 2 : 1;
+        if (h->force_mech2 == 1 || h->force_mech2 == 2) mode = h->force_mech2;
+        const size_t smem = ((size_t)P.dims[2] + P.dims[3]) * sizeof(CellRec) + A * 3 * sizeof(double);
+        const bool offsets_fit = 2LL * P.dims[1] * P.dims[2] * P.dims[3] < 0x7fffffffLL;   // 32-bit corner offsets of the range kernel
+        if (smem <= 200 * 1024 && offsets_fit) {
+            const bool tl = P.system_id == PDP_SYS_TWOLINK;
+#define MECH2R(SYS) (mode == 2 ? (a1 ? sweep_mech2_range_kernel<SYS, true, true> : sweep_mech2_range_kernel<SYS, false, true>) \
+                               : (a1 ? sweep_mech2_range_kernel<SYS, true, false> : sweep_mech2_range_kernel<SYS, false, false>))
+            k = tl ? MECH2R(PDP_SYS_TWOLINK) : MECH2R(PDP_SYS_CARTPOLE);
+#undef MECH2R
+            h->mech2_mode = mode;
+            h->smem_bytes = smem;
+        }
+    }
     h->lanes_per_node = G;
     h->fused = (void*)k;
-    const size_t A = (size_t)P.A;
     if (P.system_id == PDP_SYS_PENDULUM) {
         const size_t n1p = (size_t)((P.dims[1] + 1) & ~1);
         h->smem_bytes = (2 * n1p + 2 * (A + 2 * (size_t)G)) * sizeof(double) + 16;  // {level, 1/step} records + padded action records
@@ -279,11 +304,12 @@ static int select_fused_kernel(pdp_handle* h) {
             return fail(h, PDP_ENOTSUP, "grid too large for one launch (dims[1] too big)");
     } else {
         const size_t n2p = (size_t)((P.dims[2] + 1) & ~1), n3p = (size_t)((P.dims[3] + 1) & ~1);
-        h->smem_bytes = (2 * n2p + 2 * n3p + 4 * A) * sizeof(double) + 16;
+        if (!h->mech2_mode) h->smem_bytes = (2 * n2p + 2 * n3p + 4 * A) * sizeof(double) + 16;
         const long long plane_sz = (long long)P.dims[2] * P.dims[3];
         const long long chunks = (plane_sz * G + SWEEP_THREADS - 1) / SWEEP_THREADS;
-        if (plane_sz > 0x7fffffffLL / 16 || chunks > 65535)
+        if (plane_sz > 0x7fffffffLL / 16 || chunks > 0x7fffffffLL / 16)
             return fail(h, PDP_ENOTSUP, "grid too large for one launch (dims[2]*dims[3] too big)");
+        P.chunks = (int)chunks;
     }
     if (h->smem_bytes > 227 * 1024) return fail(h, PDP_ENOTSUP, "level/action tables exceed shared memory (227 KB)");
     cudaError_t ce = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
@@ -379,6 +405,8 @@ extern "C" int pdp_create(const pdp_problem* p, pdp_handle** out) {
     if (cudaGetDevice(&h->device) != cudaSuccess) { g_err = "cudaGetDevice failed"; return bail(PDP_ECUDA); }
     if (const char* env = getenv("PYRODP_LANES")) h->force_lanes = atoi(env);
     if (const char* env = getenv("PYRODP_GENERIC")) h->force_generic = atoi(env) != 0;
+    if (const char* env = getenv("PYRODP_MECH2"))
+        h->force_mech2 = !strcmp(env, "generic") ? 0 : !strcmp(env, "direct") ? 1 : !strcmp(env, "cache") ? 2 : -1;
 
     DevProblem& P = h->P;
     P.n = p->n; P.m = p->m; P.dof = p->n / 2; P.A = (int)A;
@@ -457,6 +485,12 @@ extern "C" int pdp_create(const pdp_problem* p, pdp_handle** out) {
             bool asc = P.all_act_ok && p->sys_par[0] > 0.0 && p->dt > 0.0;
             for (long long a = 1; a < A && asc; ++a) asc = bu[a] >= bu[a - 1];
             h->pend_mono = asc;
+        }
+        if (p->system_id == PDP_SYS_TWOLINK || p->system_id == PDP_SYS_CARTPOLE) {
+            h->plan = mech2_plan(p->system_id == PDP_SYS_TWOLINK, p->udims, bu.data(), A, P.all_act_ok, p->dt);
+            P.A0 = h->plan.A0; P.A1 = h->plan.A1;
+            P.uv_first = h->plan.uv_first; P.uv_inv_step = h->plan.uv_inv_step;
+            h->hinv_host.assign(p->sys_tab[0], p->sys_tab[0] + (size_t)p->dims[1] * 4);
         }
         if ((rc = upload(h, bu.data(), bu.size(), &P.bu)) != PDP_OK) return bail(rc);
         if ((rc = upload(h, p->gu, (size_t)A, &P.gu)) != PDP_OK) return bail(rc);
@@ -621,6 +655,36 @@ extern "C" int pdp_get_pi(pdp_handle* h, int64_t* pi_host) {
     return copy_out(h, pi_host, h->dpi, h->slab_nodes() * sizeof(long long));
 }
 
+// Node ranges of the latest J / J_next / pi (global node ids inside this handle's slab): sampled parity checks of
+// grids whose full arrays are tens of gigabytes.  which: 0 = J, 1 = J_next, 2 = pi (int64).
+extern "C" int pdp_get_range(pdp_handle* h, int32_t which, int64_t node_begin, int64_t count, void* out_host) {
+    CHECK_HANDLE(h);
+    if (!out_host || count < 0) return fail(h, PDP_EINVAL, "pdp_get_range: bad argument");
+    if (which < 0 || which > 2) return fail(h, PDP_EINVAL, "pdp_get_range: which must be 0 (J), 1 (J_next) or 2 (pi)");
+    if (which != 2 && !h->have_J) return fail(h, PDP_ESTATE, "pdp_get_range: no cost-to-go yet");
+    if (node_begin < h->P.slab_node_begin || node_begin + count > h->P.slab_node_begin + h->slab_nodes())
+        return fail(h, PDP_EINVAL, "pdp_get_range: node range outside this handle's slab");
+    if (which == 2) return copy_out(h, out_host, h->piv() + node_begin, (size_t)count * sizeof(long long));
+    return copy_out(h, out_host, h->Jv(which == 0 ? h->cur_idx : 1 - h->cur_idx) + node_begin, (size_t)count * sizeof(double));
+}
+
+// which sweep kernel this handle launches (for benchmark records and tests)
+extern "C" int pdp_kernel_info(const pdp_handle* h, char* out, int32_t len) {
+    if (!h || !out || len < 1) return fail(nullptr, PDP_EINVAL, "pdp_kernel_info: bad argument");
+    std::string name;
+    const DevProblem& P = h->P;
+    if (P.system_id == PDP_SYS_LUT) name = P.A == 1 ? "sweep_policy_kernel" : "sweep_lut_kernel";
+    else if (P.system_id == PDP_SYS_PENDULUM) name = std::string("sweep_pendulum_kernel<") + (h->pend_mono && !h->force_generic ? "mono" : "generic") + ">";
+    else {
+        const char* sys = P.system_id == PDP_SYS_TWOLINK ? "TWOLINK" : "CARTPOLE";
+        if (h->mech2_mode) name = std::string("sweep_mech2_range_kernel<") + sys + "," + (h->mech2_mode == 2 ? "cache" : "direct") + ">";
+        else name = std::string("sweep_mech2_kernel<") + sys + ">";
+    }
+    name += " G=" + std::to_string(h->lanes_per_node);
+    snprintf(out, (size_t)len, "%s", name.c_str());
+    return PDP_OK;
+}
+
 extern "C" int pdp_set_lut(pdp_handle* h, const double* x_next_host, const double* G_host) {
     CHECK_HANDLE(h);
     if (h->P.system_id != PDP_SYS_LUT) return fail(h, PDP_ESTATE, "pdp_set_lut: handle was not created with PDP_SYS_LUT");
@@ -703,10 +767,9 @@ static int launch_planes(pdp_handle* h, int p0, int p1, int stat_set, double* st
             P.plane_begin = p0;  // blockIdx.x = row of the plane range, blockIdx.y = chunk of the row
             grid = dim3((unsigned)(p1 - p0), (unsigned)(((long long)P.dims[1] * G + SWEEP_THREADS - 1) / SWEEP_THREADS), 1);
         } else {
-            const long long plane_sz = (long long)P.dims[2] * P.dims[3];
             const long long pairs = (long long)(p1 - p0) * P.dims[1];
-            if (pairs > 0x7fffffffLL) return fail(h, PDP_ENOTSUP, "grid too large for one launch");
-            grid = dim3((unsigned)pairs, (unsigned)((plane_sz * G + SWEEP_THREADS - 1) / SWEEP_THREADS), 1);
+            if (pairs * P.chunks > 0x7fffffffLL) return fail(h, PDP_ENOTSUP, "grid too large for one launch");
+            grid = dim3((unsigned)(pairs * P.chunks), 1, 1);   // chunk of the (i2,i3) plane fastest
         }
         ((fused_kernel_t)h->fused)<<<grid, SWEEP_THREADS, h->smem_bytes, stream>>>(P, Jn, Jo, h->piv(), slots, counter, stats);
     }

@@ -315,7 +315,8 @@ sweep_pendulum_kernel(const __grid_constant__ DevProblem P, const double* __rest
 // =================================================================================================
 // n = 4, 2-dof mechanical systems: 2-link arm form (pendulum.py:340 DoublePendulum,
 // manipulator.py:795 TwoLinkManipulator) and cart-pole (cartpole.py:322)
-// grid: blockIdx.x = (i0,i1) plane of the slab, blockIdx.y = chunk of the (i2,i3) plane
+// grid: 1-D, blockIdx.x = plane * chunks + chunk with the chunk of the (i2,i3) plane fastest, so that the blocks
+// resident at any time share a few (i0,i1) planes of J in L2 (P.chunks = blocks per plane)
 //
 // Measured alternatives that did NOT pay (profiles/r01h_variants.txt): two actions per iteration with
 // interleaved 16-corner blends (more registers, fewer resident warps, the L1 data pipe — ~65
@@ -350,10 +351,13 @@ sweep_mech2_kernel(const __grid_constant__ DevProblem P, const double* __restric
 
     // block-uniform part of the node index
     const int plane_sz = N2 * N3;                                  // checked on the host: < 2^31
-    const long long pl = P.plane_begin + (long long)blockIdx.x;   // (i0,i1) pair, C order
+    const unsigned chunks = (unsigned)P.chunks;
+    const unsigned pl_local = blockIdx.x / chunks;
+    const unsigned chunk = blockIdx.x - pl_local * chunks;
+    const long long pl = P.plane_begin + (long long)pl_local;    // (i0,i1) pair, C order
     const int i0 = (int)(pl / N1);
     const int i1 = (int)(pl - (long long)i0 * N1);
-    const int r = (int)(((unsigned)blockIdx.y * SWEEP_THREADS + threadIdx.x) / G);  // (i2,i3) within the plane
+    const int r = (int)((chunk * SWEEP_THREADS + threadIdx.x) / G);  // (i2,i3) within the plane
     const int g = threadIdx.x % G;
     const bool active = r < plane_sz;
     const long long node = pl * plane_sz + r;

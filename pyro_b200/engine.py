@@ -71,6 +71,19 @@ class Engine:
         self._ck(self.lib.pdp_get_pi(self.h, out.ctypes.data))
         return out
 
+    def get_range(self, which, node_begin, count):
+        """J ('J'), J_next ('J_next') or pi ('pi') of the global nodes [node_begin, node_begin + count) of this slab."""
+        code = {"J": 0, "J_next": 1, "pi": 2}[which]
+        out = np.empty(int(count), dtype=np.int64 if code == 2 else np.float64)
+        self._ck(self.lib.pdp_get_range(self.h, code, int(node_begin), int(count), out.ctypes.data))
+        return out
+
+    @property
+    def kernel_info(self):
+        buf = C.create_string_buffer(160)
+        self._ck(self.lib.pdp_kernel_info(self.h, buf, 160))
+        return buf.value.decode()
+
     def set_lut(self, x_next, G):
         x_next = np.ascontiguousarray(x_next, dtype=np.float64)
         G = np.ascontiguousarray(G, dtype=np.float64)

@@ -103,6 +103,17 @@ static inline unsigned long long atomicMax(unsigned long long* a, unsigned long 
 }
 static inline unsigned int atomicAdd(unsigned int* a, unsigned int v) { return __atomic_fetch_add(a, v, __ATOMIC_SEQ_CST); }
 
+// saturating double -> int conversions (cvt.rpi / cvt.rmi .s32.f64: NaN -> 0)
+static inline int emu_sat_int(double v) {
+    if (!(v == v)) return 0;
+    if (v >= 2147483647.0) return 2147483647;
+    if (v <= -2147483648.0) return (int)(-2147483647 - 1);
+    return (int)v;
+}
+static inline int __double2int_ru(double x) { return emu_sat_int(std::ceil(x)); }
+static inline int __double2int_rd(double x) { return emu_sat_int(std::floor(x)); }
+using std::fabs;
+
 // CUDA's overloaded min / max
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }

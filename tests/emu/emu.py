@@ -16,7 +16,7 @@ def load():
     if _lib is None:
         srcs = [os.path.join(HERE, f) for f in ("emu_main.cpp", "cuda_emu.h", "build.sh")]
         root = os.path.dirname(os.path.dirname(HERE))
-        srcs += [os.path.join(root, "pyro_b200", "csrc", f) for f in ("pyrodp_device.cuh", "sweep_fused.cuh", "table_kernels.cuh")]
+        srcs += [os.path.join(root, "pyro_b200", "csrc", f) for f in ("pyrodp_device.cuh", "sweep_fused.cuh", "table_kernels.cuh", "sweep_mech2.cuh", "mech2_plan.h")]
         if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
             subprocess.check_call(["bash", os.path.join(HERE, "build.sh")])
         _lib = C.CDLL(LIB)
@@ -26,19 +26,30 @@ def load():
         _lib.emu_sweep_planes.argtypes = [C.c_void_p] * 5 + [C.c_int] * 4
         _lib.emu_lut_sweep.restype = C.c_int
         _lib.emu_lut_sweep.argtypes = [C.c_void_p] * 7 + [C.c_int]
+        _lib.emu_mech2_evals.restype = C.c_longlong
+        _lib.emu_mech2_evals.argtypes = [C.c_int]
         _lib.emu_terminal.restype = C.c_int
         _lib.emu_terminal.argtypes = [C.c_void_p] * 3
     return _lib
 
 
-def sweep(problem, J_next, lanes=1, force_generic=False):
+MECH2_MODES = {None: 0, "generic": 1, "direct": 2, "cache": 3}
+
+
+def _mode(force_generic, mech2):
+    """Kernel selection code of emu_sweep*: 0 = as the library selects, 1 = order-agnostic kernels, 2 / 3 = the 4-D range
+    kernel with direct cells / the cached cell."""
+    return 1 if force_generic else MECH2_MODES[mech2]
+
+
+def sweep(problem, J_next, lanes=1, force_generic=False, mech2=None):
     """One backup of the whole grid by the emulated kernel: (J, pi, [j_max, delta_max, delta_min])."""
     J_next = np.ascontiguousarray(J_next, dtype=np.float64)
     J = np.empty(problem.N)
     pi = np.empty(problem.N, dtype=np.int64)
     stats = np.empty(3)
     rc = load().emu_sweep(C.addressof(problem.c), J_next.ctypes.data, J.ctypes.data, pi.ctypes.data, stats.ctypes.data,
-                          int(lanes), int(bool(force_generic)))
+                          int(lanes), _mode(force_generic, mech2))
     if rc != 0:
         raise RuntimeError(f"emu_sweep failed ({rc})")
     return J, pi, stats
@@ -69,13 +80,18 @@ def terminal(problem):
     return J, pi
 
 
-def sweep_planes(problem, J_next, J, pi, p0, p1, lanes=1, force_generic=False):
+def sweep_planes(problem, J_next, J, pi, p0, p1, lanes=1, force_generic=False, mech2=None):
     """Backup of axis-0 planes [p0, p1) only, written into the full-size arrays J / pi: what one rank (or one
     boundary / interior launch of it) computes.  Returns the statistics triple of those planes."""
     assert J_next.dtype == np.float64 and J.dtype == np.float64 and pi.dtype == np.int64
     stats = np.empty(3)
     rc = load().emu_sweep_planes(C.addressof(problem.c), J_next.ctypes.data, J.ctypes.data, pi.ctypes.data, stats.ctypes.data,
-                                 int(lanes), int(bool(force_generic)), int(p0), int(p1))
+                                 int(lanes), _mode(force_generic, mech2), int(p0), int(p1))
     if rc != 0:
         raise RuntimeError(f"emu_sweep_planes failed ({rc})")
     return stats
+
+
+def mech2_evals(reset=True):
+    """(node, action) pairs the range kernel actually evaluated since the last reset (test instrumentation)."""
+    return int(load().emu_mech2_evals(int(reset)))

@@ -126,6 +126,11 @@ void emu_launch(emu_uint3 grid, emu_uint3 block, const std::function<void()>& bo
 #include "gen/pyrodp_device.cuh"
 #include "gen/sweep_fused.cuh"
 #include "gen/table_kernels.cuh"
+#define MECH2_COUNT_EVALS
+long long mech2_evals_done = 0;
+extern "C" long long emu_mech2_evals(int reset) { long long v = mech2_evals_done; if (reset) mech2_evals_done = 0; return v; }
+#include "gen/sweep_mech2.cuh"
+#include "gen/mech2_plan.h"
 
 typedef void (*fused_kernel_t)(const DevProblem, const double*, double*, long long*, unsigned long long*, unsigned int*, double*);
 
@@ -146,6 +151,7 @@ struct HostProblem {
     DevProblem P{};
     std::vector<std::vector<double>> keep;
     bool mono = false;
+    Mech2Plan plan{};
     const double* hold(const double* src, size_t n) { keep.emplace_back(src, src + n); return keep.back().data(); }
 };
 
@@ -191,6 +197,11 @@ static void fill(const pdp_problem* p, HostProblem& H) {
         for (long long a = 1; a < A && asc; ++a) asc = bu[a] >= bu[a - 1];
         H.mono = asc;
     }
+    if (p->system_id == PDP_SYS_TWOLINK || p->system_id == PDP_SYS_CARTPOLE) {
+        H.plan = mech2_plan(p->system_id == PDP_SYS_TWOLINK, p->udims, bu.data(), A, P.all_act_ok, p->dt);
+        P.A0 = H.plan.A0; P.A1 = H.plan.A1;
+        P.uv_first = H.plan.uv_first; P.uv_inv_step = H.plan.uv_inv_step;
+    }
     P.bu = H.hold(bu.data(), bu.size());
     P.gu = H.hold(p->gu, (size_t)A);
 }
@@ -206,7 +217,8 @@ extern "C" int emu_sweep_planes(const pdp_problem* p, const double* J_next, doub
         DevProblem& P = H.P;
         const int G = lanes;
         const bool a1 = P.alpha_is_one != 0, nd = (P.system_id == PDP_SYS_PENDULUM) && P.par[1] == 0.0;
-        const bool mono = H.mono && !force_generic;
+        // force_generic: 0 = what the library selects, 1 = order-agnostic kernels, 2 / 3 = range kernel with direct cells / cached cell
+        const bool mono = H.mono && force_generic != 1;
         fused_kernel_t k = nullptr;
         if (G == 1) k = a1 ? fused_for<1, true>(P.system_id, nd, mono) : fused_for<1, false>(P.system_id, nd, mono);
         else if (G == 4) k = a1 ? fused_for<4, true>(P.system_id, nd, mono) : fused_for<4, false>(P.system_id, nd, mono);
@@ -221,8 +233,18 @@ extern "C" int emu_sweep_planes(const pdp_problem* p, const double* J_next, doub
             grid = {(unsigned)(p1 - p0), (unsigned)(((long long)P.dims[1] * G + SWEEP_THREADS - 1) / SWEEP_THREADS), 1};
         } else {
             P.plane_begin = (long long)p0 * P.dims[1];
-            grid = {(unsigned)((p1 - p0) * P.dims[1]),
-                    (unsigned)(((long long)P.dims[2] * P.dims[3] * G + SWEEP_THREADS - 1) / SWEEP_THREADS), 1};
+            P.chunks = (int)(((long long)P.dims[2] * P.dims[3] * G + SWEEP_THREADS - 1) / SWEEP_THREADS);
+            grid = {(unsigned)((p1 - p0) * P.dims[1] * P.chunks), 1, 1};
+            if (G == 1 && H.plan.ok && force_generic != 1) {   // pyrodp.cu select_fused_kernel
+                const double cell2 = (P.ub[2] - P.lb[2]) / (P.dims[2] - 1), cell3 = (P.ub[3] - P.lb[3]) / (P.dims[3] - 1);
+                int mode = mech2_cells_per_action(H.plan, p->sys_tab[0], P.dims[1], P.dt, cell2, cell3) < 0.7 ? 2 : 1;
+                if (force_generic == 2 || force_generic == 3) mode = force_generic - 1;
+                const bool tl = P.system_id == PDP_SYS_TWOLINK;
+#define MECH2R(SYS) (mode == 2 ? (a1 ? sweep_mech2_range_kernel<SYS, true, true> : sweep_mech2_range_kernel<SYS, false, true>) \
+                               : (a1 ? sweep_mech2_range_kernel<SYS, true, false> : sweep_mech2_range_kernel<SYS, false, false>))
+                k = tl ? MECH2R(PDP_SYS_TWOLINK) : MECH2R(PDP_SYS_CARTPOLE);
+#undef MECH2R
+            }
         }
         std::vector<unsigned long long> slots(3 * STATS_SLOTS, 0);
         unsigned int counter = 0;

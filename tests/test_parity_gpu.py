@@ -430,3 +430,73 @@ def test_policy_evaluation_matches_reference_goldens(name):
     pb.alpha, pb.verbose = case.get("alpha", 1.0), False
     pb.compute_steps(kb)
     assert np.array_equal(pb.J, gold[f"Jbase_{kb}"])
+
+
+# ---- the 4-D range kernel (sweep_mech2.cuh): every variant against the C oracle ----------------------------------
+@pytest.mark.parametrize("mode", ["generic", "direct", "cache"])
+@pytest.mark.parametrize("name,case", [
+    ("cartpole_41", dict(system="CartPole", x_grid_dim=[31, 33, 41, 43], u_grid_dim=[51], xbar=[0.0, float(np.pi), 0.0, 0.0], INF=1000.0)),
+    ("twolink_33", dict(system="TwoLinkManipulator", x_grid_dim=[31, 29, 33, 37], u_grid_dim=[21, 21], INF=1000.0)),
+    ("twolink_soft_33", dict(CASES["twolink_soft"], x_grid_dim=[31, 29, 33, 37], u_grid_dim=[9, 7])),
+    ("dpend_ex_35", dict(CASES["dpend_example"], x_grid_dim=[33, 31, 35, 37], u_grid_dim=[31, 31])),
+    ("dpend_inf_cost", dict(CASES["dpend_example"], x_grid_dim=[21, 23, 25, 27], u_grid_dim=[5, 7], INF=float("inf"))),
+])
+def test_range_kernel_variants_equal_c_oracle(monkeypatch, name, case, mode):
+    """PYRODP_MECH2 pins the 4-D kernel variant: the order-agnostic kernel, the range kernel with direct cells and with the
+    cached cell.  One lane per node (PYRODP_LANES=1), rough J, whole grid compared bit for bit."""
+    monkeypatch.setenv("PYRODP_MECH2", mode)
+    monkeypatch.setenv("PYRODP_LANES", "1")
+    _, grid, cf = build_case(case)
+    P = problem.extract(grid, cf, case.get("alpha", 1.0))
+    eng = Engine(P)
+    want = {"generic": "sweep_mech2_kernel<", "direct": ",direct>", "cache": ",cache>"}[mode]
+    assert want in eng.kernel_info and eng.lanes_per_node == 1, eng.kernel_info
+    J0 = np.random.default_rng(4).uniform(0, 300, P.N)
+    eng.set_J(J0)
+    st = eng.sweep(1)
+    J1, pi1 = eng.get_J(), eng.get_pi()
+    Jr, pr = c_oracle.sweep_fused(P, J0)
+    assert np.array_equal(J1, Jr) and np.array_equal(pi1, pr), (name, mode, int((pi1 != pr).sum()))
+    d = J1 - J0
+    if np.isfinite(J1).all():
+        assert st[0, 0] == J1.max() and st[0, 1] == d.max() and st[0, 2] == d.min()
+    eng.close()
+
+
+def _sampled_ranges(P, rng, count, width):
+    """Node ranges for sampled checks: random ones plus the first / last nodes, the middle of the grid, and the seams of an
+    8-way slab decomposition of axis 0 (the ranges straddle the plane boundary)."""
+    plane = P.N // P.dims[0]
+    starts = [int(s) for s in rng.integers(0, P.N - width, count)] + [0, P.N - width, plane * (P.dims[0] // 2) - width // 2]
+    starts += [plane * (r * P.dims[0] // 8) - width // 2 for r in range(1, 8)]
+    return starts
+
+
+@pytest.mark.parametrize("wl", ["cfg3", "cfg4", "cfg5"])
+def test_full_size_4d_configs_sampled_against_oracle(wl):
+    """BASELINE configs 3, 4, 5 AT FULL SIZE (TwoLinkManipulator 101^4 x 21^2, CartPole 151^4 x 51, DoublePendulum
+    201^4 x 31^2 with the example's bounds): J after two sweeps from h(x) is the input, one more sweep on the GPU, and
+    >= 24 + 10 node ranges of 256 nodes (incl. first/last planes and the seams of an 8-rank slab layout) must equal the
+    C oracle's backup of the same J_next bit for bit (J and pi)."""
+    from bench import WORKLOADS
+    case = WORKLOADS[wl]
+    _, grid, cf = build_case(case)
+    P = problem.extract(grid, cf, 1.0)
+    eng = Engine(P)
+    assert "range_kernel" in eng.kernel_info, eng.kernel_info
+    eng.eval_terminal_cost()
+    eng.sweep(2)
+    J_next = eng.get_J()              # full host copy: the oracle reads the corners it needs from it
+    st = eng.sweep(1)
+    rng = np.random.default_rng(7)
+    bad = 0
+    for lo in _sampled_ranges(P, rng, 24, 256):
+        Jr, pr = c_oracle.sweep_fused(P, J_next, lo, lo + 256)
+        Jg, pg = eng.get_range("J", lo, 256), eng.get_range("pi", lo, 256)
+        assert np.array_equal(eng.get_range("J_next", lo, 256), J_next[lo:lo + 256])
+        if not (np.array_equal(Jg, Jr) and np.array_equal(pg, pr)):
+            bad += 1
+            print(wl, "range", lo, "J mismatches", int((Jg != Jr).sum()), "pi mismatches", int((pg != pr).sum()))
+    assert bad == 0
+    assert np.isfinite(st).all() and st[0, 0] >= 0.0
+    eng.close()
