@@ -135,8 +135,8 @@ int pdp_set_J(pdp_handle* h, const double* J_host);
 int pdp_get_J(pdp_handle* h, double* J_host);       /* slab doubles  */
 int pdp_get_J_next(pdp_handle* h, double* J_host);  /* slab doubles  */
 int pdp_get_pi(pdp_handle* h, int64_t* pi_host);    /* slab int64    */
-/* `count` values starting at GLOBAL node id node_begin (inside the handle's slab) of J (which = 0), J_next (1;
- * doubles) or pi (2; int64): J[s0:s1] / pi[s0:s1] of the reference's arrays without moving the whole grid —
+/* `count` values starting at GLOBAL node id node_begin of J (which = 0), J_next (1; doubles; any node of the planes the
+ * handle holds, halo included) or pi (2; int64; inside the handle's slab): J[s0:s1] / pi[s0:s1] of the reference's arrays without moving the whole grid —
  * what sampled parity checks and look-ups on 10^9-node grids need */
 int pdp_get_range(pdp_handle* h, int32_t which, int64_t node_begin, int64_t count, void* out_host);
 
@@ -162,6 +162,10 @@ int pdp_sweep_collect(pdp_handle* h, pdp_stats* stats_out, int32_t max_out, int3
  * needs no exchange for this one sweep, and must refresh its halo (pdp_exchange_current or pdp_set_J) before
  * device-resident sweeps continue.  On a single GPU the handle is afterwards as after pdp_set_J + pdp_sweep(1). */
 int pdp_sweep_host(pdp_handle* h, const double* J_next_host, double* J_host, int64_t* pi_host, pdp_stats* stats_out);
+
+/* pdp_sweep_host for a rank of a sharded run: J_held_host holds ONLY the planes [alloc_begin, alloc_end) the handle
+ * keeps (pdp_slab_layout), so no rank needs the full (N,) array in host memory */
+int pdp_sweep_host_local(pdp_handle* h, const double* J_held_host, double* J_host, int64_t* pi_host, pdp_stats* stats_out);
 
 /* LUT mode (system_id == PDP_SYS_LUT): the generic, bit-exact path for arbitrary user systems.
  * x_next: (N_slab, A, n) float64 as discretizer.py:349, G: (N_slab, A) float64 as

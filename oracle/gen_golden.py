@@ -24,31 +24,7 @@ from tests.cases import CASES, POLICY_CASES, LinearFeedback  # noqa: E402
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
-def build_reference(ns, case):
-    cls = {"SinglePendulum": ns.pendulum.SinglePendulum, "DoublePendulum": ns.pendulum.DoublePendulum,
-           "TwoLinkManipulator": ns.manipulator.TwoLinkManipulator, "CartPole": ns.cartpole.CartPole}[case["system"]]
-    sys_ = cls()
-    for key in ("x_lb", "x_ub", "u_lb", "u_ub"):
-        if key in case:
-            getattr(sys_, key)[:] = case[key]
-    for key, val in case.get("sys_params", {}).items():
-        setattr(sys_, key, val)
-    grid = ns.discretizer.GridDynamicSystem(sys_, case["x_grid_dim"], case["u_grid_dim"], case.get("dt", 0.05))
-    if case.get("cost", "quadratic") == "quadratic":
-        cf = ns.costfunction.QuadraticCostFunction.from_sys(sys_)
-        for key in ("Q", "R", "S"):
-            if key in case:
-                setattr(cf, key, np.diag(np.array(case[key], float)) if np.ndim(case[key]) == 1 else np.array(case[key], float))
-    else:
-        cf = ns.costfunction.TimeCostFunction(np.array(case["xbar"], float))
-    if "xbar" in case:
-        cf.xbar = np.array(case["xbar"], float)
-    for key in ("INF", "EPS"):
-        if key in case:
-            setattr(cf, key, case[key])
-    dp = ns.dynamicprogramming.DynamicProgrammingWithLookUpTable(grid, cf)
-    dp.alpha = case.get("alpha", 1.0)
-    return sys_, grid, cf, dp
+build_reference = ref_loader.build_reference
 
 
 def main():

@@ -9,8 +9,10 @@ pyro/analysis/graphical.py:10-12) and matplotlib is not installed in this image,
 in-memory ``MagicMock`` modules are injected for it before the import.
 Plot methods become no-ops; never pass ``animate_*=True``.
 
-The reference is looked up in ``$PYRO_REF`` then ``/root/reference``.  It does NOT exist on
-the GPU box: callers must check :func:`available` and skip.
+The reference is looked up in ``$PYRO_REF``, then ``/root/reference`` (this container only), then
+``baseline/_ref`` — the unmodified package installed by
+``pip install --no-index --no-build-isolation --no-deps --target baseline/_ref <copy of /root/reference>``
+(git-ignored, but it travels to the GPU box).  Callers must check :func:`available` and skip.
 """
 import contextlib
 import io
@@ -18,7 +20,8 @@ import os
 import sys
 from unittest import mock
 
-_CANDIDATES = [os.environ.get("PYRO_REF", ""), "/root/reference"]
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_CANDIDATES = [os.environ.get("PYRO_REF", ""), "/root/reference", os.path.join(_ROOT, "baseline", "_ref")]
 
 _MPL = ["matplotlib", "matplotlib.pyplot", "matplotlib.animation", "matplotlib.colors",
         "matplotlib.cm", "matplotlib.ticker", "matplotlib.patches", "matplotlib.backends",
@@ -69,3 +72,35 @@ def quiet():
     """The reference prints a line per sweep / table build; silence it in tests."""
     with contextlib.redirect_stdout(io.StringIO()):
         yield
+
+
+def build_reference(ns, case, lut=True):
+    """Instantiate a parity / benchmark case (plain data, tests/cases.py) on the REAL reference classes:
+    (sys, grid_sys, cost_function, dp).  ``lut=False`` builds the grid without look-up tables and returns the base
+    class DynamicProgramming (per-pair sys.f calls, dynamicprogramming.py:195-236)."""
+    import numpy as np
+    cls = {"SinglePendulum": ns.pendulum.SinglePendulum, "DoublePendulum": ns.pendulum.DoublePendulum,
+           "TwoLinkManipulator": ns.manipulator.TwoLinkManipulator, "CartPole": ns.cartpole.CartPole}[case["system"]]
+    sys_ = cls()
+    for key in ("x_lb", "x_ub", "u_lb", "u_ub"):
+        if key in case:
+            getattr(sys_, key)[:] = case[key]
+    for key, val in case.get("sys_params", {}).items():
+        setattr(sys_, key, val)
+    grid = ns.discretizer.GridDynamicSystem(sys_, case["x_grid_dim"], case["u_grid_dim"], case.get("dt", 0.05), lut)
+    if case.get("cost", "quadratic") == "quadratic":
+        cf = ns.costfunction.QuadraticCostFunction.from_sys(sys_)
+        for key in ("Q", "R", "S"):
+            if key in case:
+                setattr(cf, key, np.diag(np.array(case[key], float)) if np.ndim(case[key]) == 1 else np.array(case[key], float))
+    else:
+        cf = ns.costfunction.TimeCostFunction(np.array(case["xbar"], float))
+    if "xbar" in case:
+        cf.xbar = np.array(case["xbar"], float)
+    for key in ("INF", "EPS"):
+        if key in case:
+            setattr(cf, key, case[key])
+    klass = ns.dynamicprogramming.DynamicProgrammingWithLookUpTable if lut else ns.dynamicprogramming.DynamicProgramming
+    dp = klass(grid, cf)
+    dp.alpha = case.get("alpha", 1.0)
+    return sys_, grid, cf, dp

@@ -58,6 +58,7 @@ SIGNATURES = {
     "pdp_sweep_enqueue": (C.c_int, [C.c_void_p]),
     "pdp_sweep_collect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
     "pdp_sweep_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pdp_sweep_host_local": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pdp_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "pdp_comm_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32]),
     "pdp_exchange_current": (C.c_int, [C.c_void_p]),

@@ -42,13 +42,3 @@ static inline Mech2Plan mech2_plan(int twolink, const int* udims, const double* 
     p.ok = 1;
     return p;
 }
-
-// Typical displacement of x_next[2], x_next[3] between consecutive inner actions, in cells: |inv(H)[.,cv]| * step * dt / cell.
-// Small values mean most actions stay in the cached interpolation cell (the corner values are kept in registers then).
-static inline double mech2_cells_per_action(const Mech2Plan& p, const double* Hinv_tab, int n1, double dt, double cell2, double cell3) {
-    if (!p.ok || n1 <= 0) return 1e30;
-    double s2 = 0.0, s3 = 0.0;
-    for (int i = 0; i < n1; ++i) { s2 += fabs(Hinv_tab[4 * i + p.cv]); s3 += fabs(Hinv_tab[4 * i + 2 + p.cv]); }
-    const double du = 1.0 / p.uv_inv_step;
-    return (s2 / n1) * du * dt / cell2 + (s3 / n1) * du * dt / cell3;
-}

@@ -93,6 +93,12 @@ __global__ void halo_wait_kernel(const unsigned int* flags, unsigned int want, i
     __threadfence_system();
 }
 
+// test hook: occupy the stream for about `cycles` SM clocks
+__global__ void delay_kernel(long long cycles) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < cycles) __nanosleep(200);
+}
+
 // =================================================================================================
 // Host side: handle + C ABI
 // =================================================================================================
@@ -136,10 +142,10 @@ struct pdp_handle {
     int policy_blocks = 0;        // one resident wave of sweep_policy_kernel blocks
     bool pend_mono = false;       // pendulum: x_next[1] is non-decreasing along the action list (see sweep_fused.cuh, MONO)
     bool force_generic = false;   // test hook (PYRODP_GENERIC=1): use the order-agnostic action loop anyway
-    int mech2_mode = 0;           // 4-D fused systems: 0 order-agnostic kernel, 1 range kernel (direct cells), 2 range kernel (cached cell)
-    int force_mech2 = -1;         // test / A-B hook (PYRODP_MECH2=generic|direct|cache)
+    int mech2_mode = 0;           // 4-D fused systems: 0 order-agnostic kernel, 1 range-skipping kernel
+    int force_mech2 = -1;         // test / A-B hook (PYRODP_MECH2=generic|range)
+    int test_interior_delay_us = 0;   // test hook (PYRODP_TEST_INTERIOR_DELAY_US): spin before the interior planes of a sharded sweep
     Mech2Plan plan{};             // action-table structure the range kernel relies on
-    std::vector<double> hinv_host;  // inv(H) table (4 per axis-1 level), kept for the cell-displacement estimate
     void* fused = nullptr;        // selected fused kernel instantiation
     // multi-GPU (one process per GPU): NCCL communicator, side stream for the halo exchange
     void* comm = nullptr;
@@ -278,19 +284,13 @@ static int select_fused_kernel(pdp_handle* h) {
     // 4-D systems, one lane per node: the range-skipping kernel when the action table has the structure it relies on
     h->mech2_mode = 0;
     if (P.system_id != PDP_SYS_PENDULUM && G == 1 && h->plan.ok && !h->force_generic && h->force_mech2 != 0) {
-        const double cell2 = (P.ub[2] - P.lb[2]) / (P.dims[2] - 1), cell3 = (P.ub[3] - P.lb[3]) / (P.dims[3] - 1);
-        const double cells = mech2_cells_per_action(h->plan, h->hinv_host.data(), P.dims[1], P.dt, cell2, cell3);
-        int mode = cells < 0.7 ? 2 : 1;
-        if (h->force_mech2 == 1 || h->force_mech2 == 2) mode = h->force_mech2;
-        const size_t smem = ((size_t)P.dims[2] + P.dims[3]) * sizeof(CellRec) + A * 3 * sizeof(double);
+        const size_t n2p = (size_t)((P.dims[2] + 1) & ~1), n3p = (size_t)((P.dims[3] + 1) & ~1);
+        const size_t smem = (2 * n2p + 2 * n3p + 3 * A) * sizeof(double) + 16;
         const bool offsets_fit = 2LL * P.dims[1] * P.dims[2] * P.dims[3] < 0x7fffffffLL;   // 32-bit corner offsets of the range kernel
         if (smem <= 200 * 1024 && offsets_fit) {
-            const bool tl = P.system_id == PDP_SYS_TWOLINK;
-#define MECH2R(SYS) (mode == 2 ? (a1 ? sweep_mech2_range_kernel<SYS, true, true> : sweep_mech2_range_kernel<SYS, false, true>) \
-                               : (a1 ? sweep_mech2_range_kernel<SYS, true, false> : sweep_mech2_range_kernel<SYS, false, false>))
-            k = tl ? MECH2R(PDP_SYS_TWOLINK) : MECH2R(PDP_SYS_CARTPOLE);
-#undef MECH2R
-            h->mech2_mode = mode;
+            if (P.system_id == PDP_SYS_TWOLINK) k = a1 ? sweep_mech2_range_kernel<PDP_SYS_TWOLINK, true> : sweep_mech2_range_kernel<PDP_SYS_TWOLINK, false>;
+            else k = a1 ? sweep_mech2_range_kernel<PDP_SYS_CARTPOLE, true> : sweep_mech2_range_kernel<PDP_SYS_CARTPOLE, false>;
+            h->mech2_mode = 1;
             h->smem_bytes = smem;
         }
     }
@@ -405,8 +405,9 @@ extern "C" int pdp_create(const pdp_problem* p, pdp_handle** out) {
     if (cudaGetDevice(&h->device) != cudaSuccess) { g_err = "cudaGetDevice failed"; return bail(PDP_ECUDA); }
     if (const char* env = getenv("PYRODP_LANES")) h->force_lanes = atoi(env);
     if (const char* env = getenv("PYRODP_GENERIC")) h->force_generic = atoi(env) != 0;
+    if (const char* env = getenv("PYRODP_TEST_INTERIOR_DELAY_US")) h->test_interior_delay_us = atoi(env);
     if (const char* env = getenv("PYRODP_MECH2"))
-        h->force_mech2 = !strcmp(env, "generic") ? 0 : !strcmp(env, "direct") ? 1 : !strcmp(env, "cache") ? 2 : -1;
+        h->force_mech2 = !strcmp(env, "generic") ? 0 : !strcmp(env, "range") ? 1 : -1;
 
     DevProblem& P = h->P;
     P.n = p->n; P.m = p->m; P.dof = p->n / 2; P.A = (int)A;
@@ -490,7 +491,6 @@ extern "C" int pdp_create(const pdp_problem* p, pdp_handle** out) {
             h->plan = mech2_plan(p->system_id == PDP_SYS_TWOLINK, p->udims, bu.data(), A, P.all_act_ok, p->dt);
             P.A0 = h->plan.A0; P.A1 = h->plan.A1;
             P.uv_first = h->plan.uv_first; P.uv_inv_step = h->plan.uv_inv_step;
-            h->hinv_host.assign(p->sys_tab[0], p->sys_tab[0] + (size_t)p->dims[1] * 4);
         }
         if ((rc = upload(h, bu.data(), bu.size(), &P.bu)) != PDP_OK) return bail(rc);
         if ((rc = upload(h, p->gu, (size_t)A, &P.gu)) != PDP_OK) return bail(rc);
@@ -662,8 +662,11 @@ extern "C" int pdp_get_range(pdp_handle* h, int32_t which, int64_t node_begin, i
     if (!out_host || count < 0) return fail(h, PDP_EINVAL, "pdp_get_range: bad argument");
     if (which < 0 || which > 2) return fail(h, PDP_EINVAL, "pdp_get_range: which must be 0 (J), 1 (J_next) or 2 (pi)");
     if (which != 2 && !h->have_J) return fail(h, PDP_ESTATE, "pdp_get_range: no cost-to-go yet");
-    if (node_begin < h->P.slab_node_begin || node_begin + count > h->P.slab_node_begin + h->slab_nodes())
-        return fail(h, PDP_EINVAL, "pdp_get_range: node range outside this handle's slab");
+    // J / J_next: any node of the planes the handle holds (slab + halo); pi: the slab only
+    const long long lo = which == 2 ? h->P.slab_node_begin : (long long)h->alloc_begin * h->plane;
+    const long long hi = which == 2 ? h->P.slab_node_begin + h->slab_nodes() : (long long)h->alloc_end * h->plane;
+    if (node_begin < lo || node_begin + count > hi)
+        return fail(h, PDP_EINVAL, "pdp_get_range: node range outside the planes this handle holds");
     if (which == 2) return copy_out(h, out_host, h->piv() + node_begin, (size_t)count * sizeof(long long));
     return copy_out(h, out_host, h->Jv(which == 0 ? h->cur_idx : 1 - h->cur_idx) + node_begin, (size_t)count * sizeof(double));
 }
@@ -677,7 +680,7 @@ extern "C" int pdp_kernel_info(const pdp_handle* h, char* out, int32_t len) {
     else if (P.system_id == PDP_SYS_PENDULUM) name = std::string("sweep_pendulum_kernel<") + (h->pend_mono && !h->force_generic ? "mono" : "generic") + ">";
     else {
         const char* sys = P.system_id == PDP_SYS_TWOLINK ? "TWOLINK" : "CARTPOLE";
-        if (h->mech2_mode) name = std::string("sweep_mech2_range_kernel<") + sys + "," + (h->mech2_mode == 2 ? "cache" : "direct") + ">";
+        if (h->mech2_mode) name = std::string("sweep_mech2_range_kernel<") + sys + ">";
         else name = std::string("sweep_mech2_kernel<") + sys + ">";
     }
     name += " G=" + std::to_string(h->lanes_per_node);
@@ -939,18 +942,27 @@ static int sharded_sweep_enqueue(pdp_handle* h, double* dst) {
                                                  20000000000LL /* ~10 s */);
         CUDA_TRY(h, cudaGetLastError());
     }
-    if ((h->exchange_mode == 1 || h->exchange_mode == 3) && h->overlap && b + hi < e - lo) {
+    // Peer-store mode: the neighbours store their next sweep's planes into THIS rank's J[cur] halo as soon as they have
+    // this rank's flag, which is published after the boundary kernels.  The interior kernel must therefore never read
+    // a halo plane: with halo_lo != halo_hi (asymmetric velocity bounds) a boundary of halo_hi planes at the low end
+    // would leave interior planes that still reach below the slab — so both boundaries are max(lo, hi) planes thick.
+    // (NCCL mode orders the receive after the interior through ev_boundary / the stream, and keeps the thin boundaries.)
+    int blo = hi, bhi = lo;   // planes computed first at the low / high end of the slab
+    if (h->exchange_mode == 3) blo = bhi = std::max(lo, hi);
+    if ((h->exchange_mode == 1 || h->exchange_mode == 3) && h->overlap && b + blo < e - bhi) {
         // Boundary planes + their exchange on the high-priority side stream, interior planes on the
         // main stream: the two kernels share the SMs (no serialised tail), the boundary blocks are
         // scheduled first, and the exchange (NCCL send/recv, or the peer-store kernel) runs under the
         // interior planes — the neighbours' flags are up long before their next sweep asks for them.
         CUDA_TRY(h, cudaEventRecord(h->ev_boundary, h->stream));            // previous sweep (and its exchange) done
         CUDA_TRY(h, cudaStreamWaitEvent(h->comm_stream, h->ev_boundary, 0));
-        if ((rc = launch_planes(h, b, b + hi, 1, sets + 3, h->comm_stream)) != PDP_OK) return rc;
-        if ((rc = launch_planes(h, e - lo, e, 2, sets + 6, h->comm_stream)) != PDP_OK) return rc;
+        if ((rc = launch_planes(h, b, b + blo, 1, sets + 3, h->comm_stream)) != PDP_OK) return rc;
+        if ((rc = launch_planes(h, e - bhi, e, 2, sets + 6, h->comm_stream)) != PDP_OK) return rc;
         if ((rc = exchange(h, 1 - h->cur_idx, h->comm_stream)) != PDP_OK) return rc;
         CUDA_TRY(h, cudaEventRecord(h->ev_comm, h->comm_stream));
-        if ((rc = launch_planes(h, b + hi, e - lo, 0, sets)) != PDP_OK) return rc;
+        if (h->test_interior_delay_us > 0)   // test hook: hold the interior back so that a racing neighbour would be caught
+            delay_kernel<<<1, 1, 0, h->stream>>>((long long)h->test_interior_delay_us * 2000LL);
+        if ((rc = launch_planes(h, b + blo, e - bhi, 0, sets)) != PDP_OK) return rc;
         CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
         stats_fold_kernel<<<1, 1, 0, h->stream>>>(sets, 3, dst);
     } else {
@@ -1050,7 +1062,7 @@ extern "C" int pdp_sweep(pdp_handle* h, int32_t n_sweeps, pdp_stats* stats_out) 
 // Enqueue the whole pipeline of one host-array sweep; every stream it uses has rejoined h->stream when it
 // returns, and the per-chunk statistics land in the handle's pinned host buffer.  Runs either directly or
 // under stream capture (then nothing executes and the work becomes a CUDA graph).
-static int host_pipeline_enqueue(pdp_handle* h, const double* J_next_host, double* J_host, int64_t* pi_host, int C) {
+static int host_pipeline_enqueue(pdp_handle* h, const double* J_next_host, long long host_plane0, double* J_host, int64_t* pi_host, int C) {
     // upload chunks partition the planes the handle holds (slab + halo), backup chunks the planes it computes
     std::vector<int> ub(C + 1), sb(C + 1);
     for (int i = 0; i <= C; ++i) {
@@ -1071,7 +1083,7 @@ static int host_pipeline_enqueue(pdp_handle* h, const double* J_next_host, doubl
     for (int i = 1; i < K; ++i) CUDA_TRY(h, cudaStreamWaitEvent(cs[i], h->ev_start, 0));
     for (int i = 0; i < C; ++i) {
         const size_t cnt = (size_t)(ub[i + 1] - ub[i]) * h->plane;
-        if (cnt) CUDA_TRY(h, cudaMemcpyAsync(Jc + (size_t)(ub[i] - h->alloc_begin) * h->plane, J_next_host + (size_t)ub[i] * h->plane,
+        if (cnt) CUDA_TRY(h, cudaMemcpyAsync(Jc + (size_t)(ub[i] - h->alloc_begin) * h->plane, J_next_host + (size_t)(ub[i] - host_plane0) * h->plane,
                                              cnt * sizeof(double), cudaMemcpyHostToDevice, h->h2d_stream));
         CUDA_TRY(h, cudaEventRecord(h->ev_up[i], h->h2d_stream));
     }
@@ -1113,7 +1125,21 @@ static bool is_pinned_host(const void* p) {
     return a.type == cudaMemoryTypeHost;
 }
 
+static int sweep_host_impl(pdp_handle* h, const double* J_next_host, long long host_plane0, double* J_host, int64_t* pi_host,
+                           pdp_stats* stats_out);
+
 extern "C" int pdp_sweep_host(pdp_handle* h, const double* J_next_host, double* J_host, int64_t* pi_host, pdp_stats* stats_out) {
+    return sweep_host_impl(h, J_next_host, 0, J_host, pi_host, stats_out);
+}
+
+// The same with a host input that holds ONLY the planes this handle keeps (slab + halo, pdp_slab_layout: planes
+// [alloc_begin, alloc_end)): what a rank of a sharded run passes, so that no rank needs the full (N,) array in host memory.
+extern "C" int pdp_sweep_host_local(pdp_handle* h, const double* J_held_host, double* J_host, int64_t* pi_host, pdp_stats* stats_out) {
+    return sweep_host_impl(h, J_held_host, h ? h->alloc_begin : 0, J_host, pi_host, stats_out);
+}
+
+static int sweep_host_impl(pdp_handle* h, const double* J_next_host, long long host_plane0, double* J_host, int64_t* pi_host,
+                           pdp_stats* stats_out) {
     CHECK_HANDLE(h);
     if (!J_next_host || !J_host || !pi_host) return fail(h, PDP_EINVAL, "pdp_sweep_host: null pointer");
     if (h->slab_end <= h->slab_begin) return fail(h, PDP_ESTATE, "pdp_sweep_host: this handle computes no planes");
@@ -1158,7 +1184,7 @@ extern "C" int pdp_sweep_host(pdp_handle* h, const double* J_next_host, double* 
             // (the legacy default stream cannot be captured: then the direct path runs)
             cudaError_t ce = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
             if (ce == cudaSuccess) {
-                rc = host_pipeline_enqueue(h, J_next_host, J_host, pi_host, C);
+                rc = host_pipeline_enqueue(h, J_next_host, host_plane0, J_host, pi_host, C);
                 ce = cudaStreamEndCapture(h->stream, &graph);
             }
             h->launches = launches0;
@@ -1188,7 +1214,7 @@ extern "C" int pdp_sweep_host(pdp_handle* h, const double* J_next_host, double* 
         }
     }
     if (!use_graph) {
-        int rc = host_pipeline_enqueue(h, J_next_host, J_host, pi_host, C);
+        int rc = host_pipeline_enqueue(h, J_next_host, host_plane0, J_host, pi_host, C);
         if (rc != PDP_OK) return rc;
     }
     h->cur_idx = 1 - h->cur_idx;

@@ -13,11 +13,17 @@
 //     arithmetic — the estimate only decides what is skipped, never a value).  Skipped pairs are Q = INF
 //     (dynamicprogramming.py:228); np.argmin's first-index rule is kept by remembering the first skipped /
 //     out-of-box index and merging INF at that index after the loop.
-//   * CartPole: consecutive actions move x_next by a quarter of a cell, so the 16 corner values of the
-//     current (k2,k3) cell stay in registers (CACHE) and are gathered again only when the cell changes.
-//   * DoublePendulum at the example's bounds: 1-3 cells per action; the cell is computed directly
-//     (arithmetic guess + one 32-byte record {lo, hi, hi-lo, 1/(hi-lo)} from shared memory that verifies it),
-//     and an in-cell x_next needs no separate box test.
+//   * What binds all three configurations is the L1 data pipe (ncu r02b: l1tex__data_pipe_lsu_wavefronts 91-99 % of
+//     peak, FP64 pipe 27-47 %): ~56 wavefronts per warp-eval for the 16 LDG.64 gathers (2 is the floor of a 256-byte
+//     warp access, unaligned segments and the lanes' different (c0,c1) planes make it 3.5) and, in the first version,
+//     23 more for per-lane 32-byte cell records and per-lane action records in shared memory.  Hence: the action
+//     loops are WARP-UNIFORM (every lane evaluates the same action at the same time, so the lanes' gathers are
+//     neighbours in memory and the action records are broadcasts; a lane outside its own bracket idles), and the
+//     level / reciprocal tables are plain arrays read with conflict-free LDS.64.
+//   * The cell of an action-dependent axis is computed directly (arithmetic guess, verified against the level
+//     table exactly as scipy's search decides it); an in-cell x_next needs no separate box test.  Keeping the
+//     16 corner values of the current cell in registers for the cart-pole (a quarter of a cell per action) was
+//     measured slower (r02a: 298 vs 254 ms at cfg4): the lanes of a warp change cells at different actions.
 // Blocks are rasterised chunk-fastest (consecutive blocks = consecutive 128-node chunks of ONE (i0,i1) plane),
 // so the ~600 resident blocks share a handful of J planes in L2 instead of 600 different ones
 // (ncu r01b: 7.3x the compulsory DRAM reads with the plane-fastest order).
@@ -39,8 +45,6 @@ __device__ __forceinline__ const T* opaque_ptr(const T* p) {
 #endif
     return p;
 }
-
-struct __align__(16) CellRec { double lo, hi, den, rinv; };   // one interpolation cell of an axis
 
 // first out-of-box index bookkeeping: NONE = no INF entry in this node's Q row so far
 #define MECH2_NONE 0x7fffffff
@@ -76,7 +80,7 @@ struct __align__(16) CellRec { double lo, hi, den, rinv; };   // one interpolati
 // base pointers of the first version cost eight registers, re-deriving them four integer instructions per row).
 #define MECH2_CORNER_PTR(i) (b00 + (o + ((((i) >> 2) & 1) ? plane_sz : 0) + (((i) >> 3) ? n1ps : 0) + ((((i) >> 1) & 1) ? N3 : 0)) + ((i) & 1))
 
-template <int SYS, bool ALPHA1, bool CACHE>
+template <int SYS, bool ALPHA1>
 __global__ void __launch_bounds__(SWEEP_THREADS, MECH2R_MIN_BLOCKS)
 sweep_mech2_range_kernel(const __grid_constant__ DevProblem P, const double* __restrict__ Jn, double* __restrict__ Jo,
                          long long* __restrict__ pi, unsigned long long* __restrict__ partials, unsigned int* counter,
@@ -84,20 +88,15 @@ sweep_mech2_range_kernel(const __grid_constant__ DevProblem P, const double* __r
     extern __shared__ __align__(16) double smem[];
     constexpr int CV = (SYS == PDP_SYS_TWOLINK) ? 1 : 0;   // row of B.u that varies along the inner action index
     const int N0 = P.dims[0], N1 = P.dims[1], N2 = P.dims[2], N3 = P.dims[3], A = P.A, A0 = P.A0, A1 = P.A1;
-    CellRec* s_c2 = (CellRec*)smem;             // [N2]  (entry N2-1 unused)
-    CellRec* s_c3 = s_c2 + N2;                  // [N3]
-    double2* s_act = (double2*)(s_c3 + N3);     // [A] {B.u[0], B.u[1]}
-    double* s_gu = (double*)(s_act + A);        // [A] du'R du
-    for (int i = threadIdx.x; i < N2; i += blockDim.x) {
-        const double lo = __ldg(P.level[2] + i), hi = __ldg(P.level[2] + min(i + 1, N2 - 1));
-        CellRec r; r.lo = lo; r.hi = hi; r.den = hi - lo; r.rinv = __ldg(P.rinv[2] + i);
-        s_c2[i] = r;
-    }
-    for (int i = threadIdx.x; i < N3; i += blockDim.x) {
-        const double lo = __ldg(P.level[3] + i), hi = __ldg(P.level[3] + min(i + 1, N3 - 1));
-        CellRec r; r.lo = lo; r.hi = hi; r.den = hi - lo; r.rinv = __ldg(P.rinv[3] + i);
-        s_c3[i] = r;
-    }
+    const int N2p = (N2 + 1) & ~1, N3p = (N3 + 1) & ~1;
+    double* s_lev2 = smem;                       // [N2p] levels of axis 2
+    double* s_rinv2 = s_lev2 + N2p;              // [N2p] correctly rounded 1/(lev[k+1]-lev[k])
+    double* s_lev3 = s_rinv2 + N2p;              // [N3p]
+    double* s_rinv3 = s_lev3 + N3p;              // [N3p]
+    double2* s_act = (double2*)(s_rinv3 + N3p);  // [A] {B.u[0], B.u[1]}
+    double* s_gu = (double*)(s_act + A);         // [A] du'R du
+    for (int i = threadIdx.x; i < N2; i += blockDim.x) { s_lev2[i] = __ldg(P.level[2] + i); s_rinv2[i] = __ldg(P.rinv[2] + i); }
+    for (int i = threadIdx.x; i < N3; i += blockDim.x) { s_lev3[i] = __ldg(P.level[3] + i); s_rinv3[i] = __ldg(P.rinv[3] + i); }
     for (int i = threadIdx.x; i < A; i += blockDim.x) {
         s_act[i] = make_double2(__ldg(P.bu + 2 * i), __ldg(P.bu + 2 * i + 1));
         s_gu[i] = __ldg(P.gu + i);
@@ -112,201 +111,179 @@ sweep_mech2_range_kernel(const __grid_constant__ DevProblem P, const double* __r
     const long long pl = P.plane_begin + (long long)pl_local;     // (i0,i1) pair, C order
     const int i0 = (int)(pl / N1);
     const int i1 = (int)(pl - (long long)i0 * N1);
-    const int r = (int)(chunk * SWEEP_THREADS + threadIdx.x);      // (i2,i3) within the plane
-    const bool active = r < plane_sz;
+    const int r_raw = (int)(chunk * SWEEP_THREADS + threadIdx.x);  // (i2,i3) within the plane
+    const bool active = r_raw < plane_sz;
+    const int r = min(r_raw, plane_sz - 1);   // lanes past the end of the plane shadow its last node: the action loops are
+                                               // warp-uniform (votes inside), their result is discarded
     const long long node = pl * plane_sz + r;
-    Stats3 st = stats_identity();
     const double PINF = __longlong_as_double(0x7ff0000000000000LL);
+
+    const int i2 = r / N3;
+    const int i3 = r - i2 * N3;
+    const double q0 = __ldg(P.level[0] + i0), q1 = __ldg(P.level[1] + i1);
+    const double dq0 = s_lev2[i2], dq1 = s_lev3[i3];
+    const double dt = P.dt;
+
+    // position rows of x_next are action independent: dq*dt + q
+    const double xn0 = dq0 * dt + q0;
+    const double xn1 = dq1 * dt + q1;
+    const bool pos_ok = !(xn0 < P.lb[0] || xn0 > P.ub[0] || xn1 < P.lb[1] || xn1 > P.ub[1]);
+    const bool live = active && pos_ok;     // this lane evaluates actions
+    // (for a lane that is not live the cells below are clamped garbage; its bracket is empty, nothing is read through them)
+    const int c0 = find_cell(P.level[0], N0, xn0, P.lb[0], P.inv_step[0]);
+    const int c1 = find_cell(P.level[1], N1, xn1, P.lb[1], P.inv_step[1]);
+    const double lo0 = __ldg(P.level[0] + c0), hi0 = __ldg(P.level[0] + c0 + 1);
+    const double lo1 = __ldg(P.level[1] + c1), hi1 = __ldg(P.level[1] + c1 + 1);
+    const double y0 = (xn0 - lo0) / (hi0 - lo0);
+    const double y1 = (xn1 - lo1) / (hi1 - lo1);
+    // _evaluate_linear weight-first association: w = (((1*w0)*w1)*w2)*w3 (_rgi.py:543-546)
+    const double w00 = (1.0 - y0) * (1.0 - y1), w01 = (1.0 - y0) * y1;
+    const double w10 = y0 * (1.0 - y1), w11 = y0 * y1;
+    const double* __restrict__ b00 = opaque_ptr(Jn + ((long long)c0 * N1 + c1) * plane_sz);
+    const int n1ps = N1 * plane_sz;     // checked on the host: 2 * N1 * N2 * N3 < 2^31
+
+    // ---- state-only dynamics terms: C(q,dq) dq, g(q), d(q,dq), inv(H(q)) ----
+    const double* __restrict__ Hi = P.tab[0] + 4 * i1;
+    const double H00 = __ldg(Hi), H01 = __ldg(Hi + 1), H10 = __ldg(Hi + 2), H11 = __ldg(Hi + 3);
+    double cd0, cd1, g0, g1, d0, d1;
+    if (SYS == PDP_SYS_TWOLINK) {
+        const double h = __ldg(P.tab[1] + i1);
+        const double C00 = (-h) * dq1, C10 = h * dq0, C01 = (-h) * (dq0 + dq1);
+        cd0 = mv2(C00, C01, dq0, dq1);
+        cd1 = mv2(C10, 0.0, dq0, dq1);
+        const double* __restrict__ Gq = P.tab[2] + 2 * ((long long)i0 * N1 + i1);
+        g0 = __ldg(Gq); g1 = __ldg(Gq + 1);
+        d0 = mv2(P.par[0], 0.0, dq0, dq1);
+        d1 = mv2(0.0, P.par[1], dq0, dq1);
+    } else {  // CARTPOLE
+        const double C01 = __ldg(P.tab[1] + i1) * dq1;
+        cd0 = mv2(0.0, C01, dq0, dq1);
+        cd1 = mv2(0.0, 0.0, dq0, dq1);
+        g0 = 0.0; g1 = __ldg(P.tab[2] + i1);
+        d0 = 0.0; d1 = 0.0;
+    }
+
+    // ---- state-only stage cost ----
+    const double dx[4] = {q0 - P.xbar[0], q1 - P.xbar[1], dq0 - P.xbar[2], dq1 - P.xbar[3]};
+    double gx = 1.0;
+    if (P.cost_id == PDP_COST_QUADRATIC) gx = quad_form<4>(P.Q, dx);
+    const bool ontarget = P.ontarget_check && (norm2<4>(dx) < P.EPS);
+    const double dt_cost = ontarget ? 0.0 : dt;
+    const double alpha = P.alpha;
+
+    // ---- bracket of the inner indices whose x_next[2], x_next[3] can lie inside the box ----
+    // x_next[k] = (hv_k * r_v + ho_k * r_o) * dt + dq_k with r_v ~ B.u[CV](a1) - off_v, so the index where
+    // x_next[k] = e is  (e - dq_k)/dt * S_k + Bk - (ho_k * S_k) * r_o,  S_k = inv_ustep / hv_k.
+    // An estimate only: it selects the evaluated interval; the margin mg covers its rounding.
+    const double hv2 = CV ? H01 : H00, hv3 = CV ? H11 : H10;
+    const double ho2 = CV ? H00 : H01, ho3 = CV ? H10 : H11;
+    double C2lo = -1e300, C2hi = 1e300, HA2 = 0.0, C3lo = -1e300, C3hi = 1e300, HA3 = 0.0;
+    double mg = 1e-3;   // safety margin of the bracket, in index units (the estimate's own rounding is ~1e-9 of its terms)
+    {
+        const double off_v = CV ? ((cd1 + g1) + d1) : ((cd0 + g0) + d0);
+        const double Bk = (off_v - P.uv_first) * P.uv_inv_step;
+        const double rdt = 1.0 / dt;
+        if (fabs(hv2) > 1e-6 * (fabs(H00) + fabs(H01))) {
+            const double S = P.uv_inv_step / hv2;
+            const double ca = ((P.lb[2] - dq0) * rdt) * S + Bk, cb = ((P.ub[2] - dq0) * rdt) * S + Bk;
+            C2lo = fmin(ca, cb); C2hi = fmax(ca, cb); HA2 = ho2 * S;
+            mg = mg + 1e-9 * (fabs(ca) + fabs(cb));
+        }
+        if (fabs(hv3) > 1e-6 * (fabs(H10) + fabs(H11))) {
+            const double S = P.uv_inv_step / hv3;
+            const double ca = ((P.lb[3] - dq1) * rdt) * S + Bk, cb = ((P.ub[3] - dq1) * rdt) * S + Bk;
+            C3lo = fmin(ca, cb); C3hi = fmax(ca, cb); HA3 = ho3 * S;
+            mg = mg + 1e-9 * (fabs(ca) + fabs(cb));
+        }
+    }
+
+    const double lb2 = P.lb[2], lb3 = P.lb[3], is2 = P.inv_step[2], is3 = P.inv_step[3];
+    const double gb2 = -(lb2 * is2), gb3 = -(lb3 * is3);   // cell guess = (int)fma(x, is, gb): a starting point only
+    int first_inf = MECH2_NONE;     // lowest action index whose Q is INF (skipped or out of the box)
     double best = PINF;
     int besta = MECH2_NONE;
-    if (active) {
-        const int i2 = r / N3;
-        const int i3 = r - i2 * N3;
-        const double q0 = __ldg(P.level[0] + i0), q1 = __ldg(P.level[1] + i1);
-        const double dq0 = s_c2[i2].lo, dq1 = s_c3[i3].lo;
-        const double dt = P.dt;
 
-        // position rows of x_next are action independent: dq*dt + q
-        const double xn0 = dq0 * dt + q0;
-        const double xn1 = dq1 * dt + q1;
-        const bool pos_ok = !(xn0 < P.lb[0] || xn0 > P.ub[0] || xn1 < P.lb[1] || xn1 > P.ub[1]);
-        if (pos_ok) {
-            const int c0 = find_cell(P.level[0], N0, xn0, P.lb[0], P.inv_step[0]);
-            const int c1 = find_cell(P.level[1], N1, xn1, P.lb[1], P.inv_step[1]);
-            const double lo0 = __ldg(P.level[0] + c0), hi0 = __ldg(P.level[0] + c0 + 1);
-            const double lo1 = __ldg(P.level[1] + c1), hi1 = __ldg(P.level[1] + c1 + 1);
-            const double y0 = (xn0 - lo0) / (hi0 - lo0);
-            const double y1 = (xn1 - lo1) / (hi1 - lo1);
-            const double w00 = (1.0 - y0) * (1.0 - y1), w01 = (1.0 - y0) * y1;
-            const double w10 = y0 * (1.0 - y1), w11 = y0 * y1;
-            const double* __restrict__ b00 = opaque_ptr(Jn + ((long long)c0 * N1 + c1) * plane_sz);
-            const int n1ps = N1 * plane_sz;     // checked on the host: 2 * N1 * N2 * N3 < 2^31
-
-            // ---- state-only dynamics terms: C(q,dq) dq, g(q), d(q,dq), inv(H(q)) ----
-            const double* __restrict__ Hi = P.tab[0] + 4 * i1;
-            const double H00 = __ldg(Hi), H01 = __ldg(Hi + 1), H10 = __ldg(Hi + 2), H11 = __ldg(Hi + 3);
-            double cd0, cd1, g0, g1, d0, d1;
-            if (SYS == PDP_SYS_TWOLINK) {
-                const double h = __ldg(P.tab[1] + i1);
-                const double C00 = (-h) * dq1, C10 = h * dq0, C01 = (-h) * (dq0 + dq1);
-                cd0 = mv2(C00, C01, dq0, dq1);
-                cd1 = mv2(C10, 0.0, dq0, dq1);
-                const double* __restrict__ Gq = P.tab[2] + 2 * ((long long)i0 * N1 + i1);
-                g0 = __ldg(Gq); g1 = __ldg(Gq + 1);
-                d0 = mv2(P.par[0], 0.0, dq0, dq1);
-                d1 = mv2(0.0, P.par[1], dq0, dq1);
-            } else {  // CARTPOLE
-                const double C01 = __ldg(P.tab[1] + i1) * dq1;
-                cd0 = mv2(0.0, C01, dq0, dq1);
-                cd1 = mv2(0.0, 0.0, dq0, dq1);
-                g0 = 0.0; g1 = __ldg(P.tab[2] + i1);
-                d0 = 0.0; d1 = 0.0;
-            }
-
-            // ---- state-only stage cost ----
-            const double dx[4] = {q0 - P.xbar[0], q1 - P.xbar[1], dq0 - P.xbar[2], dq1 - P.xbar[3]};
-            double gx = 1.0;
-            if (P.cost_id == PDP_COST_QUADRATIC) gx = quad_form<4>(P.Q, dx);
-            const bool ontarget = P.ontarget_check && (norm2<4>(dx) < P.EPS);
-            const double dt_cost = ontarget ? 0.0 : dt;
-            const double alpha = P.alpha;
-
-            // ---- bracket of the inner indices whose x_next[2], x_next[3] can lie inside the box ----
-            // x_next[k] = (hv_k * r_v + ho_k * r_o) * dt + dq_k with r_v ~ B.u[CV](a1) - off_v, so the index where
-            // x_next[k] = e is  (e - dq_k)/dt * S_k + Bk - (ho_k * S_k) * r_o,  S_k = inv_ustep / hv_k.
-            // An estimate only: it selects the evaluated interval; margins below cover its rounding.
-            const double hv2 = CV ? H01 : H00, hv3 = CV ? H11 : H10;
-            const double ho2 = CV ? H00 : H01, ho3 = CV ? H10 : H11;
-            double C2lo = -1e300, C2hi = 1e300, HA2 = 0.0, C3lo = -1e300, C3hi = 1e300, HA3 = 0.0;
-            double mg = 1e-3;   // safety margin of the bracket, in index units (the estimate's own rounding is ~1e-9 of its terms)
-            {
-                const double off_v = CV ? ((cd1 + g1) + d1) : ((cd0 + g0) + d0);
-                const double Bk = (off_v - P.uv_first) * P.uv_inv_step;
-                const double rdt = 1.0 / dt;
-                if (fabs(hv2) > 1e-6 * (fabs(H00) + fabs(H01))) {
-                    const double S = P.uv_inv_step / hv2;
-                    const double ca = ((P.lb[2] - dq0) * rdt) * S + Bk, cb = ((P.ub[2] - dq0) * rdt) * S + Bk;
-                    C2lo = fmin(ca, cb); C2hi = fmax(ca, cb); HA2 = ho2 * S;
-                    mg = mg + 1e-9 * (fabs(ca) + fabs(cb));
-                }
-                if (fabs(hv3) > 1e-6 * (fabs(H10) + fabs(H11))) {
-                    const double S = P.uv_inv_step / hv3;
-                    const double ca = ((P.lb[3] - dq1) * rdt) * S + Bk, cb = ((P.ub[3] - dq1) * rdt) * S + Bk;
-                    C3lo = fmin(ca, cb); C3hi = fmax(ca, cb); HA3 = ho3 * S;
-                    mg = mg + 1e-9 * (fabs(ca) + fabs(cb));
-                }
-            }
-
-            const double lb2 = P.lb[2], lb3 = P.lb[3], is2 = P.inv_step[2], is3 = P.inv_step[3];
-            const double gb2 = -(lb2 * is2), gb3 = -(lb3 * is3);   // cell guess = (int)fma(x, is, gb): a starting point only
-            int first_inf = MECH2_NONE;     // lowest action index whose Q is INF (skipped or out of the box)
-
-            // CACHE: the current cell of each action-dependent axis and its 16 corner values
-            int c2 = 0, c3 = 0;
-            CellRec e2, e3;
-            e2.lo = PINF; e2.hi = -PINF; e2.den = 1.0; e2.rinv = 1.0;   // empty cell: the first action locates it
-            e3 = e2;
-            double v[16];
-            if (CACHE) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = 0.0;
-            }
-
-            for (int a0 = 0; a0 < A0; ++a0) {
-                const int base = a0 * A1;
-                // the outer residual: row (1-CV) of B u - C dq - g - d, left to right (mechanical.py:231).  For the
-                // cart-pole g[0], d[0], d[1] are literal zeros (cartpole.py:415-437) and x - 0.0 == x bit for bit.
-                const double2 bu_o = s_act[base];
-                double r_o;
-                if (SYS == PDP_SYS_TWOLINK) r_o = ((bu_o.x - cd0) - g0) - d0;     // CV = 1: outer row 0
-                else r_o = (bu_o.y - cd1) - g1;                                  // CV = 0: outer row 1 (B.u[1] = +-0)
-                int lo, hi;
-                {
-                    const double t2 = HA2 * r_o, t3 = HA3 * r_o;
-                    const double lo_d = fmax(C2lo - t2, C3lo - t3) - mg;
-                    const double hi_d = fmin(C2hi - t2, C3hi - t3) + mg;
-                    lo = 0; hi = A1;
-                    if (lo_d > 0.0) lo = min(__double2int_ru(lo_d), A1);
-                    if (hi_d < (double)(A1 - 1)) hi = max(__double2int_rd(hi_d) + 1, 0);
-                    if (lo > 0) first_inf = min(first_inf, base);
-                    else if (hi < A1) first_inf = min(first_inf, base + hi);
-                }
+    for (int a0 = 0; a0 < A0; ++a0) {
+        const int base = a0 * A1;
+        // the outer residual: row (1-CV) of B u - C dq - g - d, left to right (mechanical.py:231).  For the
+        // cart-pole g[0], d[0], d[1] are literal zeros (cartpole.py:415-437) and x - 0.0 == x bit for bit.
+        const double2 bu_o = s_act[base];
+        double r_o;
+        if (SYS == PDP_SYS_TWOLINK) r_o = ((bu_o.x - cd0) - g0) - d0;     // CV = 1: outer row 0
+        else r_o = (bu_o.y - cd1) - g1;                                  // CV = 0: outer row 1 (B.u[1] = +-0)
+        int lo = A1, hi = 0;    // a lane that is not live has an empty bracket
+        if (live) {
+            const double t2 = HA2 * r_o, t3 = HA3 * r_o;
+            const double lo_d = fmax(C2lo - t2, C3lo - t3) - mg;
+            const double hi_d = fmin(C2hi - t2, C3hi - t3) + mg;
+            lo = 0; hi = A1;
+            if (lo_d > 0.0) lo = min(__double2int_ru(lo_d), A1);
+            if (hi_d < (double)(A1 - 1)) hi = max(__double2int_rd(hi_d) + 1, 0);
+            if (lo > 0) first_inf = min(first_inf, base);
+            else if (hi < A1) first_inf = min(first_inf, base + hi);
+        }
+        // Wide brackets (most actions stay in the box): the warp walks the UNION of its lanes' brackets in step, every
+        // lane on the same action — the gathers of the lanes are neighbours in memory and the action records are
+        // broadcasts.  Narrow brackets (TwoLinkManipulator at its default bounds: two or three of 21): each lane walks
+        // its own, the trip count is the widest lane's instead of the union's.  A warp-uniform choice per outer action.
+        const int lo_w = __reduce_min_sync(0xffffffffu, lo), hi_w = __reduce_max_sync(0xffffffffu, hi);
+        const int wmax = __reduce_max_sync(0xffffffffu, hi - lo);
+        const bool in_step = 4 * (hi_w - lo_w) <= 5 * wmax;
+        const int start = in_step ? lo_w : lo;
+        const int trip = in_step ? (hi_w - lo_w) : wmax;
 #ifdef MECH2_COUNT_EVALS   // test instrumentation (CPU emulation only): how many pairs the bracket let through
-                mech2_evals_done += (hi > lo) ? (hi - lo) : 0;
+        mech2_evals_done += (hi > lo) ? (hi - lo) : 0;
 #endif
-                for (int a1 = lo; a1 < hi; ++a1) {
-                    const int a = base + a1;
-                    const double2 bu = s_act[a];
-                    double r0, r1;
-                    if (SYS == PDP_SYS_TWOLINK) { r0 = r_o; r1 = ((bu.y - cd1) - g1) - d1; }
-                    else { r0 = bu.x - cd0; r1 = r_o; }
-                    const double ddq0 = mv2(H00, H01, r0, r1);
-                    const double ddq1 = mv2(H10, H11, r0, r1);
-                    const double x2 = ddq0 * dt + dq0;
-                    const double x3 = ddq1 * dt + dq1;
-                    double Jx;
-                    if (CACHE) {
-                        if (!(x2 >= e2.lo && x2 < e2.hi && x3 >= e3.lo && x3 < e3.hi)) {
-                            // left the cached cell: isavalidstate (system.py:198-205), then the level table decides the
-                            // cell exactly as scipy's search does, and the 16 corners are gathered again
-                            if (!(x2 >= lb2 && x2 <= P.ub[2] && x3 >= lb3 && x3 <= P.ub[3])) { first_inf = min(first_inf, a); continue; }
-                            if (!(x2 >= e2.lo && x2 < e2.hi)) {
-                                c2 = min(max((int)fma(x2, is2, gb2), 0), N2 - 2);
-                                e2 = s_c2[c2];
-                                while (x2 < e2.lo && c2 > 0) { --c2; e2 = s_c2[c2]; }
-                                while (x2 >= e2.hi && c2 < N2 - 2) { ++c2; e2 = s_c2[c2]; }
-                            }
-                            if (!(x3 >= e3.lo && x3 < e3.hi)) {
-                                c3 = min(max((int)fma(x3, is3, gb3), 0), N3 - 2);
-                                e3 = s_c3[c3];
-                                while (x3 < e3.lo && c3 > 0) { --c3; e3 = s_c3[c3]; }
-                                while (x3 >= e3.hi && c3 < N3 - 2) { ++c3; e3 = s_c3[c3]; }
-                            }
-                            const int o = c2 * N3 + c3;
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] = __ldg(MECH2_CORNER_PTR(i));
-                        }
-                        const double y2 = exact_div(x2 - e2.lo, e2.den, e2.rinv);
-                        const double y3 = exact_div(x3 - e3.lo, e3.den, e3.rinv);
-                        const double omy2 = 1.0 - y2, omy3 = 1.0 - y3;
-#define MECH2_V(i) v[i]
-                        MECH2_BLEND(MECH2_V)
-#undef MECH2_V
-                    } else {
-                        // direct: arithmetic guess, the 32-byte cell record verifies it (an in-cell x is inside the box)
-                        int k2 = min(max((int)fma(x2, is2, gb2), 0), N2 - 2);
-                        int k3 = min(max((int)fma(x3, is3, gb3), 0), N3 - 2);
-                        CellRec f2 = s_c2[k2], f3 = s_c3[k3];
-                        if (!(x2 >= f2.lo && x2 < f2.hi && x3 >= f3.lo && x3 < f3.hi)) {
-                            if (!(x2 >= lb2 && x2 <= P.ub[2] && x3 >= lb3 && x3 <= P.ub[3])) { first_inf = min(first_inf, a); continue; }
-                            while (x2 < f2.lo && k2 > 0) { --k2; f2 = s_c2[k2]; }
-                            while (x2 >= f2.hi && k2 < N2 - 2) { ++k2; f2 = s_c2[k2]; }
-                            while (x3 < f3.lo && k3 > 0) { --k3; f3 = s_c3[k3]; }
-                            while (x3 >= f3.hi && k3 < N3 - 2) { ++k3; f3 = s_c3[k3]; }
-                        }
-                        const double y2 = exact_div(x2 - f2.lo, f2.den, f2.rinv);
-                        const double y3 = exact_div(x3 - f3.lo, f3.den, f3.rinv);
-                        const double omy2 = 1.0 - y2, omy3 = 1.0 - y3;
-                        const int o = k2 * N3 + k3;
-#define MECH2_V(i) __ldg(MECH2_CORNER_PTR(i))
-                        MECH2_BLEND(MECH2_V)
-#undef MECH2_V
-                    }
-                    const double Qa = (gx + s_gu[a]) * dt_cost + (ALPHA1 ? Jx : alpha * Jx);
-                    if (Qa < best) { best = Qa; besta = a; }   // strict <, ascending a: first index wins (np.argmin)
-                }
+        for (int it = 0; it < trip; ++it) {
+            const int a1 = start + it;
+            if (a1 < lo || a1 >= hi) continue;  // outside this lane's bracket: Q = INF, already accounted for
+            const int a = base + a1;
+            const double2 bu = s_act[a];        // a broadcast when the warp is in step
+            const double gua = s_gu[a];
+            double r0, r1;
+            if (SYS == PDP_SYS_TWOLINK) { r0 = r_o; r1 = ((bu.y - cd1) - g1) - d1; }
+            else { r0 = bu.x - cd0; r1 = r_o; }
+            const double ddq0 = mv2(H00, H01, r0, r1);
+            const double ddq1 = mv2(H10, H11, r0, r1);
+            const double x2 = ddq0 * dt + dq0;
+            const double x3 = ddq1 * dt + dq1;
+            // direct cell: arithmetic guess, the level table verifies it (an in-cell x is inside the box)
+            int k2 = min(max((int)fma(x2, is2, gb2), 0), N2 - 2);
+            int k3 = min(max((int)fma(x3, is3, gb3), 0), N3 - 2);
+            double l2 = s_lev2[k2], h2 = s_lev2[k2 + 1], l3 = s_lev3[k3], h3 = s_lev3[k3 + 1];
+            if (!(x2 >= l2 && x2 < h2 && x3 >= l3 && x3 < h3)) {
+                // isavalidstate (system.py:198-205), then the level table decides the cell as scipy's search does
+                if (!(x2 >= lb2 && x2 <= P.ub[2] && x3 >= lb3 && x3 <= P.ub[3])) { first_inf = min(first_inf, a); continue; }
+                while (x2 < l2 && k2 > 0) { --k2; h2 = l2; l2 = s_lev2[k2]; }
+                while (x2 >= h2 && k2 < N2 - 2) { ++k2; l2 = h2; h2 = s_lev2[k2 + 1]; }
+                while (x3 < l3 && k3 > 0) { --k3; h3 = l3; l3 = s_lev3[k3]; }
+                while (x3 >= h3 && k3 < N3 - 2) { ++k3; l3 = h3; h3 = s_lev3[k3 + 1]; }
             }
+            const double y2 = exact_div(x2 - l2, h2 - l2, s_rinv2[k2]);
+            const double y3 = exact_div(x3 - l3, h3 - l3, s_rinv3[k3]);
+            const double omy2 = 1.0 - y2, omy3 = 1.0 - y3;
+            const int o = k2 * N3 + k3;
+            double Jx;
+#define MECH2_V(i) __ldg(MECH2_CORNER_PTR(i))
+            MECH2_BLEND(MECH2_V)
+#undef MECH2_V
+            const double Qa = (gx + gua) * dt_cost + (ALPHA1 ? Jx : alpha * Jx);
+            if (Qa < best) { best = Qa; besta = a; }   // strict <, ascending a: first index wins (np.argmin)
+        }
+    }
+    Stats3 st = stats_identity();
+    if (active) {
+        if (pos_ok) {
             // merge the INF entries of the row: np.argmin takes the lowest index among equal minima
             if (first_inf != MECH2_NONE) {
                 const double INF = P.INF;
                 if (INF < best || (INF == best && first_inf < besta)) { best = INF; besta = first_inf; }
             }
-            if (!(best < PINF)) besta = MECH2_NONE;   // nothing below +inf (cf.INF = inf): argmin of a constant row is 0
+            if (!(best < PINF)) besta = 0;   // nothing below +inf (cf.INF = inf): argmin of a constant row is 0
         } else {
-            best = P.INF;
+            best = P.INF;                    // every action leaves the box through a position row
             besta = 0;
         }
-        if (besta == MECH2_NONE) besta = 0;
         Jo[node] = best;
         pi[node] = besta;
         const double d = best - Jn[node];

@@ -71,7 +71,7 @@ class LookUpTableController:
 class DynamicProgramming:
     """Dynamic programming on a grid sys — Bellman sweeps on the GPU."""
 
-    def __init__(self, grid_sys, cost_function, final_time=0, engine_factory=None):
+    def __init__(self, grid_sys, cost_function, final_time=0, engine_factory=None, shard=False, time_varying=False):
         self.grid_sys = grid_sys
         self.sys = grid_sys.sys
         self.cf = cost_function
@@ -80,6 +80,9 @@ class DynamicProgramming:
         self.interpol_method = "linear"
         self.save_time_history = grid_sys.nodes_n <= HISTORY_MAX_NODES
         self.max_sweeps = None  # optional guard for solve_bellman_equation (hard part 7)
+        self.shard = shard      # True / a process group: slabs of the grid over the ranks of torch.distributed (one GPU each)
+        self.time_varying = time_varying  # table fallback only: rebuild x_next / G at every sweep's t, as the base class re-evaluates
+                                   # f(x,u,t) and g(x,u,t) (dynamicprogramming.py:214,223); the table class freezes them at tf
         self.verbose = True
         self.t = self.tf
         self.k = 0
@@ -100,16 +103,30 @@ class DynamicProgramming:
     def _make_engine(self, P):
         if self._engine_factory is not None:
             return self._engine_factory(self, P)
-        from . import distributed
-        if distributed.is_sharded():
-            return distributed.ShardedEngine(self.grid_sys, self.cf, self.alpha, self.interpol_method)
+        if self.shard:
+            # one process per GPU (torchrun): opt-in, because every rank must then build and drive the same planner —
+            # get_J / get_pi / parameter changes become collectives
+            from . import distributed
+            if not distributed.is_sharded():
+                raise RuntimeError("dp.shard is set but torch.distributed is not initialised with more than one rank")
+            if P.system_id == _lib.PDP_SYS_LUT:
+                raise NotImplementedError("sharded sweeps need a fused system (SinglePendulum, DoublePendulum, TwoLinkManipulator, "
+                                          "CartPole with box bounds): an arbitrary x_next_table has no a-priori halo")
+            group = None if self.shard is True else self.shard
+            return distributed.ShardedEngine(self.grid_sys, self.cf, self.alpha, self.interpol_method, group=group)
         if P.system_id == _lib.PDP_SYS_LUT:
             return self._make_lut_engine(P)
         return Engine(P)
 
+    # Which INF semantics the table fallback reproduces.  The reference's base class gives a disallowed input exactly INF
+    # (dynamicprogramming.py:230-233); its table class computes G + alpha*J(x_next) with G = INF, i.e. INF + alpha*J when the
+    # arrival state lies inside the grid (:545-549, :567).  Both are reproduced (the PolicyEvaluator pair does the same).
+    _invalid_input_is_exact_inf = True
+
     def _make_lut_engine(self, P):
         eng = Engine(P)
-        x_next, G = build_lookup_tables(self.grid_sys, self.cf, self.tf)
+        x_next, G = build_lookup_tables(self.grid_sys, self.cf, self.t if self.time_varying else self.tf,
+                                        exact_inf=self._invalid_input_is_exact_inf, use_grid_tables=not self.time_varying)
         eng.set_lut(x_next, G)
         return eng
 
@@ -178,7 +195,11 @@ class DynamicProgramming:
     def initialize_backward_step(self):
         self.k = self.k + 1
         self.t = self.t - self.grid_sys.dt
-        self._ensure_engine()
+        eng = self._ensure_engine()
+        if self.time_varying and eng.problem.system_id == _lib.PDP_SYS_LUT and hasattr(eng, "set_lut"):
+            x_next, G = build_lookup_tables(self.grid_sys, self.cf, self.t, exact_inf=self._invalid_input_is_exact_inf,
+                                            use_grid_tables=False)
+            eng.set_lut(x_next, G)
 
     def compute_backward_step(self):
         self._last_stats = self._engine.sweep(1)[0]
@@ -270,7 +291,9 @@ class DynamicProgramming:
 class DynamicProgrammingWithLookUpTable(DynamicProgramming):
     """Name kept for drop-in use: every reference example instantiates this class
     (dynamicprogramming.py:505).  Known systems run the fused on-the-fly kernel (no tables are
-    ever materialised); anything else runs the LUT-mode kernel on the reference-style tables."""
+    ever materialised); anything else runs the LUT-mode kernel on the reference-style tables, with the table class's
+    own value INF + alpha*J(x_next) where only the input is disallowed (:545-549, :567)."""
+    _invalid_input_is_exact_inf = False
 
 
 class PolicyEvaluator(DynamicProgramming):
@@ -334,23 +357,25 @@ class PolicyEvaluatorWithLookUpTable(PolicyEvaluator):
     _invalid_input_is_exact_inf = False
 
 
-def build_lookup_tables(grid_sys, cf, t=0):
+def build_lookup_tables(grid_sys, cf, t=0, exact_inf=False, use_grid_tables=True):
     """Reference-style dense tables for LUT mode: x_next (N,A,n), G (N,A) with INF folded in
-    (discretizer.py:342-376, dynamicprogramming.py:517-553).  Uses the grid's own tables when
-    it has them (a real pyro GridDynamicSystem built with lookup=True), else calls sys.f."""
+    (discretizer.py:342-376, dynamicprogramming.py:517-553).  Uses the grid's own tables when it has them (a real pyro
+    GridDynamicSystem built with lookup=True; they are evaluated at the default t), else calls sys.f(x, u, t).
+    ``exact_inf``: base-class semantics — a disallowed input costs exactly INF (dynamicprogramming.py:230-233): its table
+    entry is moved outside the box, where the interpolation returns its fill value 0."""
     sys = grid_sys.sys
     N, A, n = grid_sys.nodes_n, grid_sys.actions_n, sys.n
     X, U = grid_sys.state_from_node_id, grid_sys.input_from_action_id
-    have = all(hasattr(grid_sys, a) for a in ("x_next_table", "x_next_isok", "action_isok"))
+    have = use_grid_tables and all(hasattr(grid_sys, a) for a in ("x_next_table", "x_next_isok", "action_isok"))
     if have:
-        x_next, x_ok, a_ok = grid_sys.x_next_table, grid_sys.x_next_isok, grid_sys.action_isok
+        x_next, x_ok, a_ok = np.array(grid_sys.x_next_table, dtype=float), grid_sys.x_next_isok, grid_sys.action_isok
     else:
         x_next = np.zeros((N, A, n))
         x_ok = np.zeros((N, A), dtype=bool)
         a_ok = np.zeros((N, A), dtype=bool)
         for s in range(N):
             for a in range(A):
-                xn = sys.f(X[s, :], U[a, :]) * grid_sys.dt + X[s, :]
+                xn = sys.f(X[s, :], U[a, :], t) * grid_sys.dt + X[s, :]
                 x_next[s, a, :] = xn
                 x_ok[s, a] = sys.isavalidstate(xn)
                 a_ok[s, a] = sys.isavalidinput(X[s, :], U[a, :])
@@ -359,4 +384,6 @@ def build_lookup_tables(grid_sys, cf, t=0):
         for a in range(A):
             if a_ok[s, a] and x_ok[s, a]:
                 G[s, a] = cf.g(X[s, :], U[a, :], t) * grid_sys.dt
+    if exact_inf:
+        x_next[~np.asarray(a_ok, dtype=bool)] = np.asarray(sys.x_ub, dtype=float) + 1.0
     return x_next, G

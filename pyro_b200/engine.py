@@ -71,10 +71,15 @@ class Engine:
         self._ck(self.lib.pdp_get_pi(self.h, out.ctypes.data))
         return out
 
-    def get_range(self, which, node_begin, count):
-        """J ('J'), J_next ('J_next') or pi ('pi') of the global nodes [node_begin, node_begin + count) of this slab."""
+    def get_range(self, which, node_begin, count, out=None):
+        """J ('J'), J_next ('J_next') or pi ('pi') of the global nodes [node_begin, node_begin + count): J / J_next anywhere
+        in the planes this handle holds (halo included), pi inside its slab."""
         code = {"J": 0, "J_next": 1, "pi": 2}[which]
-        out = np.empty(int(count), dtype=np.int64 if code == 2 else np.float64)
+        dtype = np.int64 if code == 2 else np.float64
+        if out is None:
+            out = np.empty(int(count), dtype=dtype)
+        elif out.size != count or out.dtype != dtype or not out.flags.c_contiguous:
+            raise ValueError("output buffer does not match the range / dtype")
         self._ck(self.lib.pdp_get_range(self.h, code, int(node_begin), int(count), out.ctypes.data))
         return out
 
@@ -107,6 +112,16 @@ class Engine:
         J_out, pi_out = self._out(J_out, np.float64), self._out(pi_out, np.int64)
         stats = np.empty(3, dtype=np.float64)
         self._ck(self.lib.pdp_sweep_host(self.h, J_next.ctypes.data, J_out.ctypes.data, pi_out.ctypes.data, stats.ctypes.data))
+        return J_out, pi_out, stats
+
+    def sweep_host_local(self, J_held, J_out=None, pi_out=None):
+        """sweep_host for a rank of a sharded run: J_held holds only the planes [alloc_begin, alloc_end) of J_next."""
+        J_held = np.ascontiguousarray(J_held, dtype=np.float64)
+        if J_held.size != (self.alloc_end - self.alloc_begin) * self.plane:
+            raise ValueError("J_held must hold exactly the planes this handle keeps (slab + halo)")
+        J_out, pi_out = self._out(J_out, np.float64), self._out(pi_out, np.int64)
+        stats = np.empty(3, dtype=np.float64)
+        self._ck(self.lib.pdp_sweep_host_local(self.h, J_held.ctypes.data, J_out.ctypes.data, pi_out.ctypes.data, stats.ctypes.data))
         return J_out, pi_out, stats
 
     def sweep_nowait(self):

@@ -30,21 +30,52 @@ _COST_IDS = {
     "TimeCostFunction": _lib.PDP_COST_TIME,
 }
 _BOX_CHECK_OWNERS = ("ContinuousDynamicSystem", "MechanicalSystem")
+# Classes whose methods the fused kernels restate.  A system (cost function) is routed to a fused kernel only if EVERY
+# method the sweep depends on is still the one these classes define: a subclass that overrides any of them — the
+# reference's own InvertedPendulum flips the sign of g (pendulum.py:283), its Acrobot replaces B (pendulum.py:699) —
+# runs in LUT mode on tables built by its own methods instead of silently inheriting its parent's kernel.
+_SYS_METHODS = ("f", "ddq", "H", "C", "B", "g", "d", "x2q", "q2x")
+_SYS_OWNERS = {
+    "SinglePendulum": {"SinglePendulum"},
+    "DoublePendulum": {"DoublePendulum", "_TwoLinkForm"},
+    "TwoLinkManipulator": {"TwoLinkManipulator", "_TwoLinkForm", "Manipulator"},
+    "CartPole": {"CartPole"},
+}
+_SYS_BASE_OWNERS = {"MechanicalSystem", "ContinuousDynamicSystem"}
+_COST_METHODS = ("g", "h")
+_COST_BASE_OWNERS = {"CostFunction"}
 
 
-def _class_id(obj, table):
+def _owner(obj, name):
+    """Name of the class that defines obj.<name> (None if the attribute is missing or not a plain method)."""
+    fn = getattr(type(obj), name, None)
+    if fn is None:
+        return None
+    qual = getattr(fn, "__qualname__", "")
+    return qual.split(".")[0] if "." in qual else None
+
+
+def _class_id(obj, table, methods, owners_of, base_owners):
+    """(id, recognised class name) if obj is an instance of a recognised class AND none of `methods` is overridden by a
+    class the kernels do not know; (None, None) otherwise."""
     for klass in type(obj).__mro__:
-        if klass.__name__ in table:
-            return table[klass.__name__], klass.__name__
+        name = klass.__name__
+        if name in table:
+            allowed = set(owners_of(name)) | set(base_owners)
+            for m in methods:
+                own = _owner(obj, m)
+                if own is not None and own not in allowed:
+                    return None, None
+            if any(m in vars(obj) for m in methods):      # a method patched onto the instance
+                return None, None
+            return table[name], name
     return None, None
 
 
 def _uses_box_checks(sys):
     """True when isavalidstate / isavalidinput are the base-class box tests (system.py:198-215)."""
     for name in ("isavalidstate", "isavalidinput"):
-        fn = getattr(type(sys), name, None)
-        owner = getattr(fn, "__qualname__", "").split(".")[0]
-        if owner not in _BOX_CHECK_OWNERS:
+        if name in vars(sys) or _owner(sys, name) not in _BOX_CHECK_OWNERS:
             return False
     return True
 
@@ -52,8 +83,8 @@ def _uses_box_checks(sys):
 def classify(grid_sys, cf, interpol_method="linear"):
     """Return (system_id, cost_id); system_id == PDP_SYS_LUT means 'needs reference tables'."""
     sys = grid_sys.sys
-    sys_id, _ = _class_id(sys, _SYS_IDS)
-    cost_id, _ = _class_id(cf, _COST_IDS)
+    sys_id, _ = _class_id(sys, _SYS_IDS, _SYS_METHODS, lambda n: _SYS_OWNERS[n], _SYS_BASE_OWNERS)
+    cost_id, _ = _class_id(cf, _COST_IDS, _COST_METHODS, lambda n: {n}, _COST_BASE_OWNERS)
     if interpol_method != "linear":
         raise NotImplementedError("only interpol_method='linear' is accelerated (dynamicprogramming.py:131)")
     if sys_id is None or cost_id is None or not _uses_box_checks(sys):

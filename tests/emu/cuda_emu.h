@@ -90,6 +90,21 @@ static inline int __any_sync(unsigned, int pred) {
     return any != 0;
 }
 
+static inline int emu_reduce_int(int v, bool want_max) {
+    EmuGroup& w = emu_warp();
+    w.slot[emu_lane()] = (unsigned long long)(long long)v;
+    emu_barrier(w);
+    int r = (int)(long long)w.slot[0];
+    for (int i = 1; i < 32; ++i) {
+        const int x = (int)(long long)w.slot[i];
+        r = want_max ? (x > r ? x : r) : (x < r ? x : r);
+    }
+    emu_barrier(w);
+    return r;
+}
+static inline int __reduce_min_sync(unsigned, int v) { return emu_reduce_int(v, false); }
+static inline int __reduce_max_sync(unsigned, int v) { return emu_reduce_int(v, true); }
+
 // ---- memory / conversion intrinsics ----------------------------------------------------------------------
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 template <typename T> static inline T __ldcg(const T* p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }

@@ -33,12 +33,12 @@ def load():
     return _lib
 
 
-MECH2_MODES = {None: 0, "generic": 1, "direct": 2, "cache": 3}
+MECH2_MODES = {None: 0, "generic": 1, "range": 0}
 
 
 def _mode(force_generic, mech2):
-    """Kernel selection code of emu_sweep*: 0 = as the library selects, 1 = order-agnostic kernels, 2 / 3 = the 4-D range
-    kernel with direct cells / the cached cell."""
+    """Kernel selection code of emu_sweep*: 0 = as the library selects (the 4-D range kernel for one lane per node when the
+    action table allows it), 1 = the order-agnostic kernels."""
     return 1 if force_generic else MECH2_MODES[mech2]
 
 

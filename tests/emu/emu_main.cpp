@@ -217,7 +217,7 @@ extern "C" int emu_sweep_planes(const pdp_problem* p, const double* J_next, doub
         DevProblem& P = H.P;
         const int G = lanes;
         const bool a1 = P.alpha_is_one != 0, nd = (P.system_id == PDP_SYS_PENDULUM) && P.par[1] == 0.0;
-        // force_generic: 0 = what the library selects, 1 = order-agnostic kernels, 2 / 3 = range kernel with direct cells / cached cell
+        // force_generic: 0 = what the library selects, 1 = order-agnostic kernels
         const bool mono = H.mono && force_generic != 1;
         fused_kernel_t k = nullptr;
         if (G == 1) k = a1 ? fused_for<1, true>(P.system_id, nd, mono) : fused_for<1, false>(P.system_id, nd, mono);
@@ -236,14 +236,8 @@ extern "C" int emu_sweep_planes(const pdp_problem* p, const double* J_next, doub
             P.chunks = (int)(((long long)P.dims[2] * P.dims[3] * G + SWEEP_THREADS - 1) / SWEEP_THREADS);
             grid = {(unsigned)((p1 - p0) * P.dims[1] * P.chunks), 1, 1};
             if (G == 1 && H.plan.ok && force_generic != 1) {   // pyrodp.cu select_fused_kernel
-                const double cell2 = (P.ub[2] - P.lb[2]) / (P.dims[2] - 1), cell3 = (P.ub[3] - P.lb[3]) / (P.dims[3] - 1);
-                int mode = mech2_cells_per_action(H.plan, p->sys_tab[0], P.dims[1], P.dt, cell2, cell3) < 0.7 ? 2 : 1;
-                if (force_generic == 2 || force_generic == 3) mode = force_generic - 1;
-                const bool tl = P.system_id == PDP_SYS_TWOLINK;
-#define MECH2R(SYS) (mode == 2 ? (a1 ? sweep_mech2_range_kernel<SYS, true, true> : sweep_mech2_range_kernel<SYS, false, true>) \
-                               : (a1 ? sweep_mech2_range_kernel<SYS, true, false> : sweep_mech2_range_kernel<SYS, false, false>))
-                k = tl ? MECH2R(PDP_SYS_TWOLINK) : MECH2R(PDP_SYS_CARTPOLE);
-#undef MECH2R
+                if (P.system_id == PDP_SYS_TWOLINK) k = a1 ? sweep_mech2_range_kernel<PDP_SYS_TWOLINK, true> : sweep_mech2_range_kernel<PDP_SYS_TWOLINK, false>;
+                else k = a1 ? sweep_mech2_range_kernel<PDP_SYS_CARTPOLE, true> : sweep_mech2_range_kernel<PDP_SYS_CARTPOLE, false>;
             }
         }
         std::vector<unsigned long long> slots(3 * STATS_SLOTS, 0);

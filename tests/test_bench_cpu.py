@@ -25,16 +25,17 @@ def test_clock_sampler_without_nvml_reports_nulls_and_never_fails():
 
 
 def test_reference_arm_prints_one_contract_line():
-    """--impl reference: the reference's CPU path (oracle port) on the host cores, bounded sample, one JSON line."""
+    """--impl reference: the reference's CPU path on the host cores (the unmodified pyro classes when /root/reference or
+    baseline/_ref is there, else the oracle port), one JSON line."""
     env = dict(os.environ, PYTHONPATH=ROOT)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                        "--workload", "cfg1"], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+                        "--workload", "cfg1", "--no-extra"], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "state_action_evals_per_s" and d["unit"] == "evals/s"
-    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert d["higher_is_better"] is True and d["gpu_launches"] == 0
 

@@ -433,7 +433,7 @@ def test_policy_evaluation_matches_reference_goldens(name):
 
 
 # ---- the 4-D range kernel (sweep_mech2.cuh): every variant against the C oracle ----------------------------------
-@pytest.mark.parametrize("mode", ["generic", "direct", "cache"])
+@pytest.mark.parametrize("mode", ["generic", "range"])
 @pytest.mark.parametrize("name,case", [
     ("cartpole_41", dict(system="CartPole", x_grid_dim=[31, 33, 41, 43], u_grid_dim=[51], xbar=[0.0, float(np.pi), 0.0, 0.0], INF=1000.0)),
     ("twolink_33", dict(system="TwoLinkManipulator", x_grid_dim=[31, 29, 33, 37], u_grid_dim=[21, 21], INF=1000.0)),
@@ -442,14 +442,14 @@ def test_policy_evaluation_matches_reference_goldens(name):
     ("dpend_inf_cost", dict(CASES["dpend_example"], x_grid_dim=[21, 23, 25, 27], u_grid_dim=[5, 7], INF=float("inf"))),
 ])
 def test_range_kernel_variants_equal_c_oracle(monkeypatch, name, case, mode):
-    """PYRODP_MECH2 pins the 4-D kernel variant: the order-agnostic kernel, the range kernel with direct cells and with the
-    cached cell.  One lane per node (PYRODP_LANES=1), rough J, whole grid compared bit for bit."""
+    """PYRODP_MECH2 pins the 4-D kernel variant: the order-agnostic kernel or the range-skipping kernel.  One lane per node
+    (PYRODP_LANES=1), rough J, whole grid compared bit for bit."""
     monkeypatch.setenv("PYRODP_MECH2", mode)
     monkeypatch.setenv("PYRODP_LANES", "1")
     _, grid, cf = build_case(case)
     P = problem.extract(grid, cf, case.get("alpha", 1.0))
     eng = Engine(P)
-    want = {"generic": "sweep_mech2_kernel<", "direct": ",direct>", "cache": ",cache>"}[mode]
+    want = {"generic": "sweep_mech2_kernel<", "range": "sweep_mech2_range_kernel<"}[mode]
     assert want in eng.kernel_info and eng.lanes_per_node == 1, eng.kernel_info
     J0 = np.random.default_rng(4).uniform(0, 300, P.N)
     eng.set_J(J0)
