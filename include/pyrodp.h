@@ -229,6 +229,30 @@ int pdp_kernel_info(const pdp_handle* h, char* out, int32_t len);
 /* device time in ms of the last pdp_sweep() call, measured with CUDA events on the handle's stream */
 double pdp_last_sweep_ms(const pdp_handle* h);
 
+/* ---- single-process multi-GPU: one host thread drives n slab handles -------------------------------
+ * pdp_multi_create cuts axis 0 into n_parts balanced slabs, part i on CUDA device devices[i] (NULL: round-robin over
+ * all visible devices; a device may repeat — several slabs on one GPU).  p is the whole-grid descriptor (slab fields
+ * ignored).  Per sweep every part computes its boundary planes first, stores them into its neighbours' halo planes
+ * with peer copies (NVLink between GPUs) on a side stream, and computes its interior meanwhile; no NCCL, no
+ * launcher.  The pdp_multi_* calls mirror their single-handle counterparts on the FULL (N,) arrays. */
+typedef struct pdp_multi pdp_multi;
+int pdp_device_count(void);
+int pdp_multi_create(const pdp_problem* p, int32_t n_parts, const int32_t* devices, pdp_multi** out);
+int pdp_multi_destroy(pdp_multi* m);
+const char* pdp_multi_last_error(const pdp_multi* m);
+int32_t pdp_multi_parts(const pdp_multi* m);
+pdp_handle* pdp_multi_part(const pdp_multi* m, int32_t i);       /* the slab handle of part i (diagnostics, getters) */
+int32_t pdp_multi_part_device(const pdp_multi* m, int32_t i);
+int64_t pdp_multi_launch_count(const pdp_multi* m);
+int pdp_multi_eval_terminal_cost(pdp_multi* m);
+int pdp_multi_set_J(pdp_multi* m, const double* J_full);
+int pdp_multi_get(pdp_multi* m, int32_t which, void* out_full);  /* which: 0 J, 1 J_next (doubles), 2 pi (int64) */
+int pdp_multi_sweep(pdp_multi* m, int32_t n_sweeps, pdp_stats* stats_out);
+int pdp_multi_sweep_enqueue(pdp_multi* m);
+int pdp_multi_sweep_collect(pdp_multi* m, pdp_stats* stats_out, int32_t max_out, int32_t* n_out);
+int pdp_multi_get_input_from_policy(pdp_multi* m, int32_t k, double* uk_full);
+int pdp_multi_clean_infeasible_set(pdp_multi* m, double tol, int64_t default_action);
+
 #ifdef __cplusplus
 }
 #endif

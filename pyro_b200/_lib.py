@@ -74,6 +74,22 @@ SIGNATURES = {
     "pdp_slab_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "pdp_compute_halo": (C.c_int, [C.POINTER(pdp_problem), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "pdp_device_buffers": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_void_p)] * 4),
+    "pdp_device_count": (C.c_int, []),
+    "pdp_multi_create": (C.c_int, [C.POINTER(pdp_problem), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_void_p)]),
+    "pdp_multi_destroy": (C.c_int, [C.c_void_p]),
+    "pdp_multi_last_error": (C.c_char_p, [C.c_void_p]),
+    "pdp_multi_parts": (C.c_int32, [C.c_void_p]),
+    "pdp_multi_part": (C.c_void_p, [C.c_void_p, C.c_int32]),
+    "pdp_multi_part_device": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "pdp_multi_launch_count": (C.c_int64, [C.c_void_p]),
+    "pdp_multi_eval_terminal_cost": (C.c_int, [C.c_void_p]),
+    "pdp_multi_set_J": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pdp_multi_get": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "pdp_multi_sweep": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "pdp_multi_sweep_enqueue": (C.c_int, [C.c_void_p]),
+    "pdp_multi_sweep_collect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
+    "pdp_multi_get_input_from_policy": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "pdp_multi_clean_infeasible_set": (C.c_int, [C.c_void_p, C.c_double, C.c_int64]),
     "pdp_nodes": (C.c_int64, [C.c_void_p]),
     "pdp_nodes_padded": (C.c_int64, [C.c_void_p]),
     "pdp_actions": (C.c_int64, [C.c_void_p]),

@@ -50,6 +50,10 @@ __global__ void stats_fold_kernel(const double* __restrict__ sets, int nsets, do
     }
     dst[0] = a; dst[1] = b; dst[2] = -c;
 }
+// two triples that are not adjacent (interior + upper boundary of the lowest part)
+__global__ void stats_fold2_kernel(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ dst) {
+    dst[0] = fmax(a[0], b[0]); dst[1] = fmax(a[1], b[1]); dst[2] = -fmin(a[2], b[2]);
+}
 __global__ void stats_unfold_kernel(double* __restrict__ st, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) st[3 * i + 2] = -st[3 * i + 2];
@@ -1339,3 +1343,5 @@ extern "C" int pdp_test_exact_div(const double* a, const double* den, double* q_
     cudaFree(da); cudaFree(dd); cudaFree(df); cudaFree(di);
     return e == cudaSuccess ? PDP_OK : fail(nullptr, PDP_ECUDA, cudaGetErrorString(e));
 }
+
+#include "multi.cuh"

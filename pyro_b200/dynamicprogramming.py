@@ -31,7 +31,11 @@ HISTORY_MAX_NODES = 1 << 22
 
 
 class LookUpTableController:
-    """pi -> u(x) by n-linear interpolation of the per-axis input tables (dynamicprogramming.py:27-107)."""
+    """pi -> u(x) by n-linear interpolation of the per-axis input tables (dynamicprogramming.py:27-107), with the
+    StaticController surface the reference's controller inherits (pyro/control/controller.py:22-162): dimensions k/m/p,
+    name, ref_label/ref_units, r_lb/r_ub, rbar, c / cbar / t2r, forward_kinematic_lines_plus and ``ctl + sys``.
+    ``u_tables`` (one (N,) array per input axis, from pdp_get_input_from_policy) replaces the reference's O(N) Python
+    loop over get_input_from_policy (discretizer.py:616-633)."""
 
     def __init__(self, grid_sys, pi, u_tables=None):
         if grid_sys.nodes_n != pi.size:
@@ -39,6 +43,10 @@ class LookUpTableController:
         self.k, self.m, self.p = 1, grid_sys.sys.m, grid_sys.sys.n
         self.grid_sys, self.pi = grid_sys, pi
         self.name = "Tabular Controller"
+        self.ref_label = ["Ref. %d" % i for i in range(self.k)]
+        self.ref_units = [""] * self.k
+        self.r_ub = np.zeros(self.k) + 10
+        self.r_lb = np.zeros(self.k) - 10
         self.rbar = np.zeros(self.k)
         self.interpol_method = ["linear"] * self.m
         self._u_tables = u_tables
@@ -60,12 +68,45 @@ class LookUpTableController:
     def c(self, y, r, t=0):
         return self.lookup_table_selection(y)
 
-    # StaticController conveniences (pyro/control/controller.py:93-155): constant reference, feedback at it
+    # StaticController (pyro/control/controller.py:93-162): constant reference, feedback at it, closed loop by "+"
     def t2r(self, t):
         return self.rbar
 
     def cbar(self, y, t=0):
-        return self.c(y, self.rbar, t)
+        return self.c(y, self.t2r(t), t)
+
+    def forward_kinematic_lines_plus(self, x, u, t):
+        return None, None, None
+
+    def __add__(self, sys):
+        """closed_loop_system = controller + dynamic_system (controller.py:155-162): pyro's own ClosedLoopSystem."""
+        try:
+            from pyro.control.controller import ClosedLoopSystem
+        except Exception as exc:
+            raise ImportError("ctl + sys builds pyro.control.controller.ClosedLoopSystem; the pyro package is not importable "
+                              "here (closed-loop simulation is outside the accelerated path)") from exc
+        return ClosedLoopSystem(sys, self)
+
+    def plot_control_law(self, *a, **k):
+        raise NotImplementedError("plotting is outside the accelerated path; wrap the tables in pyro's own controller "
+                                  "(make_reference_controller) to use its plot helpers")
+
+
+def make_reference_controller(grid_sys, pi, u_tables):
+    """The reference's own LookUpTableController (a pyro StaticController with every plot / closed-loop helper) fed with
+    device-computed input tables, when the pyro package is importable; None otherwise."""
+    try:
+        from pyro.planning.dynamicprogramming import LookUpTableController as RefController
+    except Exception:
+        return None
+
+    class DeviceLookUpTableController(RefController):
+        def compute_interpol_functions(self):      # dynamicprogramming.py:72-83 without the per-node Python loop
+            self.u_interpol = [self.grid_sys.compute_interpolation_function(u_tables[k], self.interpol_method[k],
+                                                                            bounds_error=False, fill_value=0)
+                               for k in range(self.m)]
+
+    return DeviceLookUpTableController(grid_sys, pi)
 
 
 class DynamicProgramming:
@@ -269,8 +310,11 @@ class DynamicProgramming:
         self._J = self._pi = None
 
     def get_lookup_table_controller(self):
+        """dynamicprogramming.py:472-477.  With the pyro package importable this IS pyro's LookUpTableController (so
+        ``ctl + sys``, ``plot_control_law`` ... behave as in the reference); otherwise the mirror above."""
         u_tables = [self._engine.get_input_from_policy(k) for k in range(self.sys.m)]
-        return LookUpTableController(self.grid_sys, self.pi, u_tables)
+        ctl = make_reference_controller(self.grid_sys, self.pi, u_tables) if hasattr(self.grid_sys, "x_grid_dim") else None
+        return ctl if ctl is not None else LookUpTableController(self.grid_sys, self.pi, u_tables)
 
     def save_latest(self, name='test_data'):
         np.save(name + '_J_inf', self.J_next)

@@ -200,3 +200,130 @@ class Engine:
     @property
     def last_sweep_ms(self):
         return float(self.lib.pdp_last_sweep_ms(self.h))
+
+
+class MultiEngine:
+    """The Engine interface over n slab handles driven by ONE host thread (include/pyrodp.h, pdp_multi_*): the grid is
+    cut over axis 0, part i lives on ``devices[i]`` (default: round-robin over all visible GPUs), halo planes travel
+    by peer copies under the interior planes.  No launcher, no torch.distributed: a plain script uses every GPU."""
+
+    def __init__(self, problem: Problem, n_parts=None, devices=None):
+        self.lib = _lib.load()
+        self.problem = problem
+        self.N, self.A, self.n, self.m = problem.N, problem.A, problem.n, problem.m
+        ndev = int(self.lib.pdp_device_count())
+        if devices is not None:
+            n_parts = len(devices)
+        elif n_parts is None:
+            n_parts = max(ndev, 1)
+        dev_arr = (C.c_int32 * n_parts)(*devices) if devices is not None else None
+        h = C.c_void_p()
+        rc = self.lib.pdp_multi_create(C.byref(problem.c), int(n_parts), dev_arr, C.byref(h))
+        if rc != _lib.PDP_OK:
+            msg = self.lib.pdp_multi_last_error(None)
+            _lib.check(rc) if not msg else _raise(rc, msg.decode())
+        self.h = h
+        self.n_parts = int(self.lib.pdp_multi_parts(self.h))
+        self.devices = [int(self.lib.pdp_multi_part_device(self.h, i)) for i in range(self.n_parts)]
+        self.n0 = problem.dims[0]
+        self.plane = self.N // self.n0
+        self.slab_begin, self.slab_end, self.alloc_begin, self.alloc_end = 0, self.n0, 0, self.n0
+        self.slab_nodes = self.N
+        self.layouts = []
+        for i in range(self.n_parts):
+            lay = (C.c_int32 * 8)()
+            _lib.check(self.lib.pdp_slab_layout(self.lib.pdp_multi_part(self.h, i), lay))
+            self.layouts.append(tuple(int(v) for v in lay))
+        self.halo_lo, self.halo_hi = self.layouts[0][4], self.layouts[0][5]
+        self.lanes_per_node = self.layouts[0][7]
+        self._enqueued = 0
+
+    def _ck(self, rc):
+        if rc != _lib.PDP_OK:
+            msg = self.lib.pdp_multi_last_error(self.h)
+            _raise(rc, msg.decode() if msg else f"pdp error {rc}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pdp_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def eval_terminal_cost(self):
+        self._ck(self.lib.pdp_multi_eval_terminal_cost(self.h))
+
+    def set_J(self, J):
+        J = np.ascontiguousarray(J, dtype=np.float64)
+        if J.size != self.N:
+            raise ValueError("Grid size does not match data")
+        self._ck(self.lib.pdp_multi_set_J(self.h, J.ctypes.data))
+
+    def _get(self, which, dtype, out):
+        if out is None:
+            out = np.empty(self.N, dtype=dtype)
+        elif out.size != self.N or out.dtype != dtype or not out.flags.c_contiguous:
+            raise ValueError("output buffer does not match the grid size / dtype")
+        self._ck(self.lib.pdp_multi_get(self.h, which, out.ctypes.data))
+        return out
+
+    def get_J(self, out=None):
+        return self._get(0, np.float64, out)
+
+    def get_J_next(self, out=None):
+        return self._get(1, np.float64, out)
+
+    def get_pi(self, out=None):
+        return self._get(2, np.int64, out)
+
+    def sweep(self, n_sweeps=1):
+        stats = np.empty((max(n_sweeps, 0), 3), dtype=np.float64)
+        self._ck(self.lib.pdp_multi_sweep(self.h, int(n_sweeps), stats.ctypes.data))
+        return stats
+
+    def sweep_nowait(self):
+        self._ck(self.lib.pdp_multi_sweep_enqueue(self.h))
+        self._enqueued += 1
+
+    def collect_stats(self):
+        n = self._enqueued
+        out = np.empty((max(n, 1), 3), dtype=np.float64)
+        got = C.c_int32(0)
+        self._ck(self.lib.pdp_multi_sweep_collect(self.h, out.ctypes.data, n, C.byref(got)))
+        self._enqueued = 0
+        return out[:got.value]
+
+    def get_input_from_policy(self, k):
+        out = np.empty(self.N, dtype=np.float64)
+        self._ck(self.lib.pdp_multi_get_input_from_policy(self.h, int(k), out.ctypes.data))
+        return out
+
+    def clean_infeasible_set(self, tol, default_action):
+        self._ck(self.lib.pdp_multi_clean_infeasible_set(self.h, float(tol), int(default_action)))
+
+    @property
+    def kernel_info(self):
+        buf = C.create_string_buffer(160)
+        _lib.check(self.lib.pdp_kernel_info(self.lib.pdp_multi_part(self.h, 0), buf, 160))
+        return buf.value.decode()
+
+    @property
+    def launch_count(self):
+        return int(self.lib.pdp_multi_launch_count(self.h))
+
+
+def _raise(rc, msg):
+    if rc == _lib.PDP_EINVAL:
+        raise ValueError(msg)
+    if rc == _lib.PDP_ENOTSUP:
+        raise NotImplementedError(msg)
+    raise RuntimeError(msg)
+
+
+def device_count():
+    """Visible CUDA devices (0 without a driver); from the library, so torch is not needed."""
+    return int(_lib.load().pdp_device_count())

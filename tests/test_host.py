@@ -294,3 +294,102 @@ def test_controller_and_infeasible_cleaning_equal_the_real_reference():
         rdp.clean_infeasible_set(tol=1)
     dp.clean_infeasible_set(tol=1)
     assert np.array_equal(dp.J, rdp.J) and np.array_equal(dp.pi, rdp.pi)
+
+
+def test_classify_routes_overriding_subclasses_to_lut_mode():
+    """a subclass that overrides the dynamics or the cost must NOT inherit its parent's fused kernel."""
+    from pyro_b200 import _lib, costfunction, systems
+
+    class G:
+        pass
+
+    def ids(sys_, cf=None):
+        g = G()
+        g.sys = sys_
+        return problem.classify(g, cf or costfunction.QuadraticCostFunction.from_sys(sys_))
+
+    class Renamed(systems.SinglePendulum):          # parameters only: still the parent's equations
+        def __init__(self):
+            super().__init__()
+            self.m1 = 2.0
+
+    class FlippedGravity(systems.SinglePendulum):   # the reference's InvertedPendulum does exactly this (pendulum.py:283)
+        def g(self, q):
+            return -systems.SinglePendulum.g(self, q)
+
+    class OtherB(systems.DoublePendulum):           # ... and its Acrobot this (pendulum.py:699)
+        def B(self, q):
+            return np.array([[0.0], [1.0]])
+
+    class Obstacle(systems.CartPole):
+        def isavalidstate(self, x):
+            return bool(super().isavalidstate(x) and abs(x[0]) > 0.1)
+
+    class MyCost(costfunction.QuadraticCostFunction):
+        def g(self, x, u, t=0):
+            return 2.0 * super().g(x, u, t)
+
+    assert ids(systems.SinglePendulum()) == (_lib.PDP_SYS_PENDULUM, _lib.PDP_COST_QUADRATIC)
+    assert ids(Renamed()) == (_lib.PDP_SYS_PENDULUM, _lib.PDP_COST_QUADRATIC)
+    for s in (FlippedGravity(), OtherB(), Obstacle()):
+        assert ids(s) == (_lib.PDP_SYS_LUT, 0), type(s).__name__
+    assert ids(systems.SinglePendulum(), MyCost(2, 1)) == (_lib.PDP_SYS_LUT, 0)
+    patched = systems.CartPole()
+    patched.f = lambda x, u, t=0: np.zeros(4)       # a method patched onto the instance
+    assert ids(patched) == (_lib.PDP_SYS_LUT, 0)
+    if ref_loader.available():
+        ns = ref_loader.load()
+        real = lambda s: ids(s, ns.costfunction.QuadraticCostFunction.from_sys(s))
+        assert real(ns.pendulum.SinglePendulum())[0] == _lib.PDP_SYS_PENDULUM
+        assert real(ns.pendulum.DoublePendulum())[0] == _lib.PDP_SYS_TWOLINK
+        assert real(ns.manipulator.TwoLinkManipulator())[0] == _lib.PDP_SYS_TWOLINK
+        assert real(ns.cartpole.CartPole())[0] == _lib.PDP_SYS_CARTPOLE
+        assert real(ns.pendulum.InvertedPendulum())[0] == _lib.PDP_SYS_LUT
+        assert real(ns.pendulum.Acrobot())[0] == _lib.PDP_SYS_LUT
+
+
+def test_lookup_table_controller_has_the_static_controller_surface():
+    """what reference scripts do with dp.get_lookup_table_controller() (controller.py:22-162)."""
+    case = dict(CASES["pend_51x51x11"], x_grid_dim=[9, 7], u_grid_dim=[3])
+    _, grid, cf = build_case(case)
+    pi = np.arange(grid.nodes_n) % 3
+    ctl = dynamicprogramming.LookUpTableController(grid, pi)
+    assert (ctl.k, ctl.m, ctl.p) == (1, 1, 2) and ctl.name == "Tabular Controller"
+    assert ctl.ref_label == ["Ref. 0"] and ctl.ref_units == [""] and ctl.r_ub[0] == 10 and ctl.r_lb[0] == -10
+    x = np.array([0.3, -0.7])
+    assert np.array_equal(ctl.cbar(x), ctl.c(x, ctl.t2r(0.0))) and ctl.forward_kinematic_lines_plus(x, 0, 0) == (None, None, None)
+    if ref_loader.available():
+        ns = ref_loader.load()
+        cl = ctl + ns.pendulum.SinglePendulum()                         # pyro's own ClosedLoopSystem
+        assert type(cl).__name__ == "ClosedLoopSystem" and cl.controller is ctl
+        # with pyro importable the planner hands out pyro's LookUpTableController itself, fed with the device tables
+        rc = dynamicprogramming.make_reference_controller(grid, pi, [grid.get_input_from_policy(pi, 0)])
+        assert isinstance(rc, ns.dynamicprogramming.LookUpTableController) and np.array_equal(rc.c(x, rc.rbar), ctl.c(x, ctl.rbar))
+
+
+def test_table_fallback_reproduces_both_inf_semantics():
+    """base class = exact INF on a disallowed input (dynamicprogramming.py:230-233), table class =
+    INF + alpha*J(x_next) (:545-549,:567); f and g are evaluated at the t that is passed."""
+    from pyro_b200 import systems, costfunction, discretizer
+
+    class Picky(systems.SinglePendulum):
+        def isavalidinput(self, x, u):
+            return bool(super().isavalidinput(x, u) and not (x[0] > 0 and u[0] > 0))
+
+        def f(self, x, u, t=0):
+            return super().f(x, u, t) * (1.0 + t)
+
+    sys_ = Picky()
+    grid = discretizer.GridDynamicSystem(sys_, [7, 5], [3], 0.05)
+    cf = costfunction.QuadraticCostFunction.from_sys(sys_)
+    xa, Ga = dynamicprogramming.build_lookup_tables(grid, cf, t=0.0, exact_inf=True)
+    xb, Gb = dynamicprogramming.build_lookup_tables(grid, cf, t=0.0, exact_inf=False)
+    assert np.array_equal(Ga, Gb)
+    X, U = grid.state_from_node_id, grid.input_from_action_id
+    bad = np.array([[not sys_.isavalidinput(X[s], U[a]) for a in range(3)] for s in range(grid.nodes_n)])
+    assert bad.any() and (Ga[bad] == cf.INF).all()
+    assert (xa[bad] > sys_.x_ub).all() and np.array_equal(xa[~bad], xb[~bad])     # moved outside the box: RGI returns 0 there
+    assert not (xb[bad] > sys_.x_ub).all()
+    xt, _ = dynamicprogramming.build_lookup_tables(grid, cf, t=1.0, exact_inf=False)
+    s, a = 3, 1
+    assert np.array_equal(xt[s, a], sys_.f(X[s], U[a], 1.0) * grid.dt + X[s]) and not np.array_equal(xt[s, a], xb[s, a])

@@ -500,3 +500,56 @@ def test_full_size_4d_configs_sampled_against_oracle(wl):
     assert bad == 0
     assert np.isfinite(st).all() and st[0, 0] >= 0.0
     eng.close()
+
+
+# ---- the unmodified reference on the GPU box (baseline/_ref travels with the snapshot) ---------------------------
+from oracle import ref_loader  # noqa: E402
+
+needs_ref = pytest.mark.skipif(not ref_loader.available(), reason="reference not installed (baseline/_ref)")
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["pend_51x51x11", "pend_time_41x61x7", "dpend_example", "cartpole_swingup"])
+def test_integration_stub_on_the_real_pyro_classes(name):
+    """INTEGRATION.md's binding (pyro_b200/pyro_binding.py): a subclass of the REAL pyro DynamicProgramming over the REAL
+    GridDynamicSystem / cost function objects, one pdp_sweep_host call per sweep, against the reference's own goldens."""
+    from pyro_b200.pyro_binding import bind
+    ns = ref_loader.load()
+    case, gold = CASES[name], load_golden(name)
+    B200 = bind(ns.dynamicprogramming.DynamicProgramming)
+    with ref_loader.quiet():
+        # the real classes, no look-up tables (lookup=False): the binding never needs them
+        _, rgrid, rcf, _ = ref_loader.build_reference(ns, dict(case, x_grid_dim=[3] * len(case["x_grid_dim"])), lut=False)
+        sys_ = rgrid.sys
+        rgrid = ns.discretizer.GridDynamicSystem(sys_, case["x_grid_dim"], case["u_grid_dim"], case.get("dt", 0.05), False)
+        dp = B200(rgrid, rcf)
+        dp.alpha = case.get("alpha", 1.0)
+        assert isinstance(dp, ns.dynamicprogramming.DynamicProgramming) and np.array_equal(dp.J, gold["J0"])
+        k = 0
+        for target in case["snapshots"][:3]:
+            dp.compute_steps(target - k)          # pyro's own driver loop and finalize_backward_step
+            k = target
+            assert np.array_equal(dp.J, gold[f"J_{k}"]) and np.array_equal(dp.pi, gold[f"pi_{k}"]), (name, k)
+        assert dp.k == k and len(dp.J_list) == k + 1      # the reference's history bookkeeping ran
+    dp.close()
+
+
+@needs_ref
+@pytest.mark.parametrize("which", ["InvertedPendulum", "Acrobot"])
+def test_subclasses_that_override_the_dynamics_run_in_lut_mode_and_match_the_reference(which):
+    """pendulum.InvertedPendulum flips the sign of g, pendulum.Acrobot replaces B.  Both must run on
+    tables built by their OWN methods (LUT mode), and equal the reference's DynamicProgrammingWithLookUpTable."""
+    ns = ref_loader.load()
+    with ref_loader.quiet():
+        sys_ = getattr(ns.pendulum, which)()
+        dims, udims = ([21, 21], [5]) if which == "InvertedPendulum" else ([5, 5, 5, 5], [3])
+        rgrid = ns.discretizer.GridDynamicSystem(sys_, dims, udims, 0.05)
+        rcf = ns.costfunction.QuadraticCostFunction.from_sys(sys_)
+        rcf.INF = 300
+        rdp = ns.dynamicprogramming.DynamicProgrammingWithLookUpTable(rgrid, rcf)
+        rdp.compute_steps(6)
+    dp = dynamicprogramming.DynamicProgrammingWithLookUpTable(rgrid, rcf)
+    dp.verbose = False
+    assert dp._engine.problem.system_id == _lib.PDP_SYS_LUT
+    dp.compute_steps(6)
+    assert np.array_equal(dp.J, rdp.J) and np.array_equal(dp.pi, rdp.pi), which
