@@ -48,6 +48,10 @@ extern "C" {
 /* cost_id: which stage cost g(x,u) / terminal cost h(x) */
 #define PDP_COST_QUADRATIC 1 /* pyro/analysis/costfunction.py:100-204 QuadraticCostFunction */
 #define PDP_COST_TIME 2      /* pyro/analysis/costfunction.py:287-334 TimeCostFunction      */
+#define PDP_COST_REACH 3     /* pyro/analysis/costfunction.py:421-481 Reachability with the system's own box isavalidstate and the
+                                default norm test: g = 0 on every (in-box) node, h = 0 if ||x - xbar|| < EPS else INF.
+                                (QuadraticCostFunctionWithDomainCheck, :339-415, with the box isavalidstate IS PDP_COST_QUADRATIC
+                                on grid nodes: a node never fails the box test.)  Custom callbacks run in LUT mode. */
 
 /*
  * Problem descriptor (POD).  Everything a sweep needs, read by the host shim from the pyro

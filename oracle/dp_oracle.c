@@ -167,6 +167,7 @@ int orc_sweep_fused(const pdp_problem* p, const double* J_next, int64_t lo, int6
         for (int d = n - 1; d >= 0; --d) { ix[d] = (int)(r % p->dims[d]); r /= p->dims[d]; x[d] = p->x_level[d][ix[d]]; }
         for (int d = 0; d < n; ++d) dxb[d] = x[d] - p->xbar[d];
         double gx = (p->cost_id == PDP_COST_QUADRATIC) ? quad_form(p->Q, dxb, n) : 1.0;
+        if (p->cost_id == PDP_COST_REACH) gx = 0.0;   /* Reachability.g on an in-box node (costfunction.py:468-481) */
         int ontarget = p->ontarget_check && (norm_l2(dxb, n) < p->EPS);
         double best = INFINITY;
         int64_t besta = 0;
@@ -231,6 +232,7 @@ int orc_terminal(const pdp_problem* p, double* J_out) {
             h = quad_form(p->S, dxb, p->n);
             if (p->ontarget_check && norm_l2(dxb, p->n) < p->EPS) h = 0.0;
         }
+        if (p->cost_id == PDP_COST_REACH) h = (norm_l2(dxb, p->n) < p->EPS) ? 0.0 : p->INF;   /* costfunction.py:442-465 */
         J_out[s] = h;
     }
     return 0;

@@ -242,6 +242,22 @@ class TimeCost(QuadCost):
         return np.zeros(X.shape[:-1])
 
 
+class ReachCost(QuadCost):
+    """Reachability (costfunction.py:421-481) with the system's box isavalidstate and the default norm test: g = 0 on a node
+    inside the box (grid nodes always are), h = 0 if ||x - xbar|| < EPS else INF.  INF = 1e4, EPS = 0.2 by default."""
+
+    def __init__(self, xbar):
+        xbar = np.asarray(xbar, float)
+        super().__init__(xbar.size, 1, xbar)
+        self.INF, self.EPS = 1e4, 0.2
+
+    def g(self, X, U):
+        return np.zeros(np.broadcast_shapes(X.shape[:-1], U.shape[:-1]))
+
+    def h(self, X):
+        return np.where(self._norm(X - self.xbar) < self.EPS, 0.0, self.INF)
+
+
 # ------------------------------------------------------------------------------------------------
 # RegularGridInterpolator(method='linear', bounds_error=False, fill_value=0) restated
 # ------------------------------------------------------------------------------------------------

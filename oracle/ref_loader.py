@@ -88,18 +88,8 @@ def build_reference(ns, case, lut=True):
     for key, val in case.get("sys_params", {}).items():
         setattr(sys_, key, val)
     grid = ns.discretizer.GridDynamicSystem(sys_, case["x_grid_dim"], case["u_grid_dim"], case.get("dt", 0.05), lut)
-    if case.get("cost", "quadratic") == "quadratic":
-        cf = ns.costfunction.QuadraticCostFunction.from_sys(sys_)
-        for key in ("Q", "R", "S"):
-            if key in case:
-                setattr(cf, key, np.diag(np.array(case[key], float)) if np.ndim(case[key]) == 1 else np.array(case[key], float))
-    else:
-        cf = ns.costfunction.TimeCostFunction(np.array(case["xbar"], float))
-    if "xbar" in case:
-        cf.xbar = np.array(case["xbar"], float)
-    for key in ("INF", "EPS"):
-        if key in case:
-            setattr(cf, key, case[key])
+    from tests.cases import make_cost
+    cf = make_cost(ns.costfunction, sys_, case)
     klass = ns.dynamicprogramming.DynamicProgrammingWithLookUpTable if lut else ns.dynamicprogramming.DynamicProgramming
     dp = klass(grid, cf)
     dp.alpha = case.get("alpha", 1.0)

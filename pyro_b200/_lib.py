@@ -11,7 +11,7 @@ PDP_ABI_VERSION = 1
 PDP_MAX_N, PDP_MAX_M = 4, 2
 PDP_OK, PDP_EINVAL, PDP_ENOTSUP, PDP_ECUDA, PDP_ESTATE = 0, -1, -2, -3, -4
 PDP_SYS_LUT, PDP_SYS_PENDULUM, PDP_SYS_TWOLINK, PDP_SYS_CARTPOLE = 0, 1, 2, 3
-PDP_COST_QUADRATIC, PDP_COST_TIME = 1, 2
+PDP_COST_QUADRATIC, PDP_COST_TIME, PDP_COST_REACH = 1, 2, 3
 
 _dp = C.POINTER(C.c_double)
 

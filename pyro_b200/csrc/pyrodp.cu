@@ -366,7 +366,7 @@ extern "C" int pdp_create(const pdp_problem* p, pdp_handle** out) {
         case PDP_SYS_CARTPOLE: if (p->n != 4 || p->m != 1) return fail(nullptr, PDP_EINVAL, "CARTPOLE needs n=4, m=1"); break;
         default: return fail(nullptr, PDP_ENOTSUP, "pdp_create: unknown system_id");
     }
-    if (p->system_id != PDP_SYS_LUT && p->cost_id != PDP_COST_QUADRATIC && p->cost_id != PDP_COST_TIME)
+    if (p->system_id != PDP_SYS_LUT && p->cost_id != PDP_COST_QUADRATIC && p->cost_id != PDP_COST_TIME && p->cost_id != PDP_COST_REACH)
         return fail(nullptr, PDP_ENOTSUP, "pdp_create: unknown cost_id");
     long long N = 1, A = 1;
     for (int d = 0; d < p->n; ++d) {

@@ -157,6 +157,7 @@ sweep_pendulum_kernel(const __grid_constant__ DevProblem P, const double* __rest
     const double dx[2] = {q - P.xbar[0], dq_node - P.xbar[1]};
     double gx = 1.0;
     if (P.cost_id == PDP_COST_QUADRATIC) gx = quad_form<2>(P.Q, dx);
+    if (P.cost_id == PDP_COST_REACH) gx = 0.0;   // Reachability.g is 0 on every node inside the box (costfunction.py:468-481)
     const bool ontarget = P.ontarget_check && (norm2<2>(dx) < P.EPS);
     // g = 0 inside the target zone (costfunction.py:193-197): 0*dt == (gx+gu)*0 == +0
     const double dt_cost = ontarget ? 0.0 : dt;
@@ -415,6 +416,7 @@ sweep_mech2_kernel(const __grid_constant__ DevProblem P, const double* __restric
             const double dx[4] = {q0 - P.xbar[0], q1 - P.xbar[1], dq0 - P.xbar[2], dq1 - P.xbar[3]};
             double gx = 1.0;
             if (P.cost_id == PDP_COST_QUADRATIC) gx = quad_form<4>(P.Q, dx);
+    if (P.cost_id == PDP_COST_REACH) gx = 0.0;   // Reachability.g is 0 on every node inside the box (costfunction.py:468-481)
             const bool ontarget = P.ontarget_check && (norm2<4>(dx) < P.EPS);
 
             const double lb2 = P.lb[2], ub2 = P.ub[2], lb3 = P.lb[3], ub3 = P.ub[3];

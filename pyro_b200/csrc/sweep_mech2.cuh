@@ -167,6 +167,7 @@ sweep_mech2_range_kernel(const __grid_constant__ DevProblem P, const double* __r
     const double dx[4] = {q0 - P.xbar[0], q1 - P.xbar[1], dq0 - P.xbar[2], dq1 - P.xbar[3]};
     double gx = 1.0;
     if (P.cost_id == PDP_COST_QUADRATIC) gx = quad_form<4>(P.Q, dx);
+    if (P.cost_id == PDP_COST_REACH) gx = 0.0;   // Reachability.g is 0 on every node inside the box (costfunction.py:468-481)
     const bool ontarget = P.ontarget_check && (norm2<4>(dx) < P.EPS);
     const double dt_cost = ontarget ? 0.0 : dt;
     const double alpha = P.alpha;

@@ -191,6 +191,7 @@ __global__ void terminal_cost_kernel(const __grid_constant__ DevProblem P, doubl
         h = quad_form<N>(P.S, dx);
         if (P.ontarget_check && norm2<N>(dx) < P.EPS) h = 0.0;
     }
+    if (P.cost_id == PDP_COST_REACH) h = (norm2<N>(dx) < P.EPS) ? 0.0 : P.INF;   // Reachability.h / norm_test (costfunction.py:442-465)
     J[node] = h;
     if (node >= P.node_begin && node < P.node_end) pi[node] = 0;
 }

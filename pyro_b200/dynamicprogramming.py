@@ -23,11 +23,13 @@ import time
 import numpy as np
 
 from . import _lib, problem as _problem
-from .engine import Engine
+from .engine import Engine, MultiEngine, device_count
 
 # above this many nodes the per-sweep J/pi history (one full array each per sweep,
 # dynamicprogramming.py:255-258) defaults to off — 13 GB/sweep at 201^4
 HISTORY_MAX_NODES = 1 << 22
+# from this many nodes on a fused system is spread over every visible GPU by one host thread (pdp_multi_*)
+MULTI_MIN_NODES = 1 << 25
 
 
 class LookUpTableController:
@@ -157,7 +159,24 @@ class DynamicProgramming:
             return distributed.ShardedEngine(self.grid_sys, self.cf, self.alpha, self.interpol_method, group=group)
         if P.system_id == _lib.PDP_SYS_LUT:
             return self._make_lut_engine(P)
+        n_parts = self._multi_parts(P)
+        if n_parts > 1:
+            try:
+                return MultiEngine(P, n_parts=n_parts)
+            except ValueError:          # the halo is wider than a slab of this grid: one handle
+                pass
         return Engine(P)
+
+    @staticmethod
+    def _multi_parts(P):
+        """How many slab handles this process drives (pdp_multi_*): every visible GPU for a grid large enough to pay for
+        the halo copies, one otherwise.  PYRODP_MULTI = 0 / 1 (off), n (that many parts, round-robin over the GPUs)."""
+        import os
+        env = os.environ.get("PYRODP_MULTI")
+        if env is not None:
+            return max(int(env), 1)
+        ndev = device_count()
+        return ndev if (ndev > 1 and P.N >= MULTI_MIN_NODES) else 1
 
     # Which INF semantics the table fallback reproduces.  The reference's base class gives a disallowed input exactly INF
     # (dynamicprogramming.py:230-233); its table class computes G + alpha*J(x_next) with G = INF, i.e. INF + alpha*J when the

