@@ -63,7 +63,8 @@ def measured_peak():
 def ncu_counters(workload):
     """Per-launch counters of the sweep kernel from the committed ncu captures (profiles/traffic.json), or {}:
     dram_bytes (dram__bytes_read.sum + dram__bytes_write.sum), fp64_warp_inst (sm__inst_executed_pipe_fp64.sum),
-    warp_inst (smsp__inst_executed.sum), source."""
+    l1_wavefronts (l1tex__data_pipe_lsu_wavefronts.sum), warp_inst (smsp__inst_executed.sum), ncu_pct, source
+    (written by scripts/ncu_counters.py)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         rec = json.load(open(p)).get(workload)
@@ -508,35 +509,48 @@ def run_workload(ctx, args, wl_key, primary):
         kernel_ms = ctx.reduce([float(np.median(km))], "max")[0]
         exchange_ms = ctx.reduce([float(np.median(xm))], "max")[0]
 
-    # ---- roofline: what binds is the FP64 issue port; the HBM contract figure beside it ----
+    # ---- roofline: the unit that binds (ncu, profiles/) — FP64 issue for the 2-D kernel, the L1 data pipe for the 4-D
+    #      gathers — evaluated on THIS run's kernel time; the SURVEY 8(d) HBM contract figure and DRAM traffic beside it ----
     peak_hbm, peak_src = measured_peak()
     slab_evals = evals_per_step / world
     ncu = ncu_counters(wl_key)
     mhz = (clocks or {}).get("sm_mhz") or 1965.0
-    peak_fp64 = FP64_WARP_INST_PER_CLK_PER_SM * ctx.sms * mhz * 1e6 / 1e9            # G warp-instructions / s
-    fp64_inst = ncu.get("fp64_warp_inst")
-    achieved_fp64 = (fp64_inst / world) / (kernel_ms * 1e-3) / 1e9 if fp64_inst else None
-    contract = slab_evals * b_eval(n, A) / (kernel_ms * 1e-3) / 1e9
+    clk = ctx.sms * mhz * 1e6                                         # SM-cycles per second
+    kernel_s = kernel_ms * 1e-3
+
+    def unit(count, per_clk_per_sm, label, source):
+        if not count:
+            return None
+        ach, peak = (count / world) / kernel_s / 1e9, per_clk_per_sm * clk / 1e9
+        return {"achieved": ach, "peak": peak, "unit": label, "frac": ach / peak, "per_launch": count / world, "peak_source": source}
+    fp64 = unit(ncu.get("fp64_warp_inst"), FP64_WARP_INST_PER_CLK_PER_SM, "G FP64 warp-inst/s",
+                f"{FP64_WARP_INST_PER_CLK_PER_SM} FP64 warp-inst/clk/SM (scripts/micro/fp64_peak.cu, profiles/r01_fp64_peak_micro.txt) x {ctx.sms} SMs x {mhz:.0f} MHz")
+    l1 = unit(ncu.get("l1_wavefronts"), 1.0, "G L1 data-pipe wavefronts/s",
+              f"1 LSU wavefront/clk/SM (ncu l1tex__data_pipe_lsu_wavefronts peak) x {ctx.sms} SMs x {mhz:.0f} MHz")
+    cands = [(k, v) for k, v in (("fp64_issue", fp64), ("l1_data_pipe", l1)) if v]
+    bound, top = max(cands, key=lambda kv: kv[1]["frac"]) if cands else ("fp64_issue", None)
+    contract = slab_evals * b_eval(n, A) / kernel_s / 1e9
     dram = ncu.get("dram_bytes")
     roofline = {
-        "bound": "fp64_issue", "achieved": achieved_fp64, "peak": peak_fp64, "unit": "G FP64 warp-inst/s",
-        "frac": achieved_fp64 / peak_fp64 if achieved_fp64 else None,
+        "bound": bound, "achieved": top["achieved"] if top else None, "peak": top["peak"] if top else None,
+        "unit": top["unit"] if top else None, "frac": top["frac"] if top else None,
         "traffic": dram / world if dram else None,
         "kernel": keng.kernel_info, "kernel_ms": kernel_ms, "exchange_ms": exchange_ms,
-        "peak_source": f"{FP64_WARP_INST_PER_CLK_PER_SM} FP64 warp-inst/clk/SM (scripts/micro/fp64_peak.cu, profiles/r01_fp64_peak_micro.txt) x "
-                       f"{ctx.sms} SMs x {mhz:.0f} MHz (NVML median under load)",
-        "fp64_warp_inst_per_launch": fp64_inst / world if fp64_inst else None,
-        "fp64_inst_per_eval": fp64_inst * 32.0 / evals_per_step if fp64_inst else None,
-        "counters_source": ncu.get("source"),
+        "fp64_issue": fp64, "l1_data_pipe": l1,
+        "fp64_inst_per_eval": ncu["fp64_warp_inst"] * 32.0 / evals_per_step if ncu.get("fp64_warp_inst") else None,
+        "l1_wavefronts_per_warp_eval": ncu["l1_wavefronts"] * 32.0 / evals_per_step if ncu.get("l1_wavefronts") else None,
+        "ncu_pct": ncu.get("ncu_pct"), "counters_source": ncu.get("source"),
         "traffic_over_compulsory": (dram / (24.0 * N)) if dram else None,
         "compulsory_dram_bytes_per_launch": 24.0 * N / world,
-        "dram": {"achieved": (dram / world) / (kernel_ms * 1e-3) / 1e9, "peak": peak_hbm, "unit": "GB/s",
-                 "frac": (dram / world) / (kernel_ms * 1e-3) / 1e9 / peak_hbm} if dram else None,
+        "dram": {"achieved": (dram / world) / kernel_s / 1e9, "peak": peak_hbm, "unit": "GB/s",
+                 "frac": (dram / world) / kernel_s / 1e9 / peak_hbm} if dram else None,
         "contract": {"bound": "hbm", "achieved": contract, "peak": peak_hbm, "unit": "GB/s", "frac": contract / peak_hbm,
                      "peak_source": peak_src, "algorithmic_bytes_per_eval": b_eval(n, A),
                      "algorithmic_bytes_per_launch": slab_evals * b_eval(n, A),
                      "note": "SURVEY 8(d) contract figure: the 2^n-corner J gather counted as memory traffic; it is served by L1/L2, "
                              "so this fraction can exceed 1 and is not a bandwidth statement"},
+        "note": "counters per launch come from the committed ncu capture of the same kernel and workload (profiles/traffic.json); "
+                "time, clock and therefore every rate and fraction are this run's",
     }
 
     # ---- CPU baseline beside it (rank 0, N=1, primary workload only) -----------------------------------------

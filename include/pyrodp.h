@@ -177,6 +177,12 @@ int pdp_sweep_host_local(pdp_handle* h, const double* J_held_host, double* J_hos
  * dynamicprogramming.py:564-570 on the device. */
 int pdp_set_lut(pdp_handle* h, const double* x_next_host, const double* G_host);
 
+/* ---- step before the sweep, for callers that want the reference's dense tables (discretizer.py:342-376
+ * compute_xnext_table, dynamicprogramming.py:517-553 compute_cost_lookuptable) of a fused system without the O(N*A)
+ * Python loops: nodes [node_begin, node_begin+count), any output may be NULL.
+ * x_next: (count, A, n) float64; x_next_isok: (count, A) uint8; G: (count, A) float64 = g*dt or INF */
+int pdp_build_tables(pdp_handle* h, int64_t node_begin, int64_t count, double* x_next_host, uint8_t* x_next_isok_host, double* G_host);
+
 /* ---- step after the sweep: policy -> input tables (discretizer.py:616-633 get_input_from_policy),
  * u_k[s] = input_from_action_id[pi[s], k], computed on the device, slab doubles to host */
 int pdp_get_input_from_policy(pdp_handle* h, int32_t k, double* uk_host);

@@ -1297,6 +1297,39 @@ extern "C" int pdp_peer_attach(pdp_handle* h, const void* lower200, const void* 
     return PDP_OK;
 }
 
+// Dense look-up tables of a node range, built on the device (the step before the sweep for callers that want the
+// reference's tables: discretizer.py:342-376, dynamicprogramming.py:517-553).  Host outputs, any may be NULL:
+// x_next (count*A*n doubles), x_next_isok (count*A bytes), G (count*A doubles).
+extern "C" int pdp_build_tables(pdp_handle* h, int64_t node_begin, int64_t count, double* x_next_host, uint8_t* x_ok_host, double* G_host) {
+    CHECK_HANDLE(h);
+    if (h->P.system_id == PDP_SYS_LUT) return fail(h, PDP_ENOTSUP, "pdp_build_tables: needs a fused system (LUT-mode handles are given their tables)");
+    if (!h->P.all_act_ok) return fail(h, PDP_ENOTSUP, "pdp_build_tables: a disallowed action is folded into the B.u table; build the tables on the host");
+    if (node_begin < 0 || count < 0 || node_begin + count > h->N) return fail(h, PDP_EINVAL, "pdp_build_tables: node range outside the grid");
+    const long long pairs = count * (long long)h->A;
+    if (pairs == 0) return PDP_OK;
+    if (pairs > (1LL << 31) * 256) return fail(h, PDP_EINVAL, "pdp_build_tables: range too large for one call");
+    double *dx = nullptr, *dG = nullptr;
+    unsigned char* dok = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (x_next_host) e = cudaMalloc(&dx, (size_t)pairs * h->P.n * sizeof(double));
+    if (e == cudaSuccess && x_ok_host) e = cudaMalloc(&dok, (size_t)pairs);
+    if (e == cudaSuccess && G_host) e = cudaMalloc(&dG, (size_t)pairs * sizeof(double));
+    if (e == cudaSuccess) {
+        const unsigned blocks = (unsigned)((pairs + 255) / 256);
+        if (h->P.n == 2) build_tables_kernel<2><<<blocks, 256, 0, h->stream>>>(h->P, node_begin, count, dx, dok, dG);
+        else build_tables_kernel<4><<<blocks, 256, 0, h->stream>>>(h->P, node_begin, count, dx, dok, dG);
+        e = cudaGetLastError();
+        h->launches += 1;
+    }
+    if (e == cudaSuccess && dx) e = cudaMemcpyAsync(x_next_host, dx, (size_t)pairs * h->P.n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && dok) e = cudaMemcpyAsync(x_ok_host, dok, (size_t)pairs, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && dG) e = cudaMemcpyAsync(G_host, dG, (size_t)pairs * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(dx); cudaFree(dok); cudaFree(dG);
+    if (e != cudaSuccess) return fail(h, PDP_ECUDA, std::string("pdp_build_tables: ") + cudaGetErrorString(e));
+    return PDP_OK;
+}
+
 // u_k of this handle's slab (slab_nodes doubles)
 extern "C" int pdp_get_input_from_policy(pdp_handle* h, int32_t k, double* uk_host) {
     CHECK_HANDLE(h);

@@ -211,3 +211,75 @@ __global__ void clean_infeasible_kernel(double* __restrict__ J, long long* __res
     }
 }
 
+// ---- the step BEFORE the sweep: dense look-up tables on the device ------------------------------------------------
+// GridDynamicSystem.compute_xnext_table (discretizer.py:342-376): x_next_table[s,a,:] = f(x_s,u_a)*dt + x_s and
+// x_next_isok[s,a] = isavalidstate(x_next); DynamicProgrammingWithLookUpTable.compute_cost_lookuptable
+// (dynamicprogramming.py:517-553): G[s,a] = g(x_s,u_a)*dt where the action and the arrival state are allowed, else INF.
+// For the four fused systems, with the arithmetic of the sweep kernels (so the tables carry the reference's bits):
+// one thread per (node, action) pair of the node range [node0, node0 + count).  Any output pointer may be null.
+template <int N>
+__global__ void build_tables_kernel(const __grid_constant__ DevProblem P, long long node0, long long count,
+                                    double* __restrict__ x_next, unsigned char* __restrict__ x_ok, double* __restrict__ G) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int A = P.A;
+    if (idx >= count * A) return;
+    const long long s = idx / A;
+    const int a = (int)(idx - s * A);
+    int ix[N];
+    double x[N], dx[N];
+    long long r = node0 + s;
+#pragma unroll
+    for (int d = N - 1; d >= 0; --d) {
+        ix[d] = (int)(r % P.dims[d]);
+        r /= P.dims[d];
+        x[d] = __ldg(P.level[d] + ix[d]);
+        dx[d] = x[d] - P.xbar[d];
+    }
+    double f[N];
+    if (N == 2) {        // SinglePendulum: ddq = inv(H) (B u - C dq - g - d), C = 0 (mechanical.py:222-234, pendulum.py:80-150)
+        const double t = ((__ldg(P.bu + a) - 0.0 * x[1]) - __ldg(P.tab[0] + ix[0])) - P.par[1] * x[1];
+        f[0] = x[1];
+        f[1] = P.par[0] * t;
+    } else {
+        const double dq0 = x[2], dq1 = x[3];
+        const double* __restrict__ Hi = P.tab[0] + 4 * ix[1];
+        double cd0, cd1, g0, g1, d0, d1;
+        if (P.system_id == PDP_SYS_TWOLINK) {
+            const double h = __ldg(P.tab[1] + ix[1]);
+            const double C00 = (-h) * dq1, C10 = h * dq0, C01 = (-h) * (dq0 + dq1);
+            cd0 = mv2(C00, C01, dq0, dq1);
+            cd1 = mv2(C10, 0.0, dq0, dq1);
+            const double* __restrict__ Gq = P.tab[2] + 2 * ((long long)ix[0] * P.dims[1] + ix[1]);
+            g0 = __ldg(Gq); g1 = __ldg(Gq + 1);
+            d0 = mv2(P.par[0], 0.0, dq0, dq1);
+            d1 = mv2(0.0, P.par[1], dq0, dq1);
+        } else {
+            const double C01 = __ldg(P.tab[1] + ix[1]) * dq1;
+            cd0 = mv2(0.0, C01, dq0, dq1);
+            cd1 = mv2(0.0, 0.0, dq0, dq1);
+            g0 = 0.0; g1 = __ldg(P.tab[2] + ix[1]);
+            d0 = 0.0; d1 = 0.0;
+        }
+        const double r0 = ((__ldg(P.bu + 2 * a) - cd0) - g0) - d0;
+        const double r1 = ((__ldg(P.bu + 2 * a + 1) - cd1) - g1) - d1;
+        f[0] = dq0; f[1] = dq1;
+        f[N - 2] = mv2(__ldg(Hi), __ldg(Hi + 1), r0, r1);
+        f[N - 1] = mv2(__ldg(Hi + 2), __ldg(Hi + 3), r0, r1);
+    }
+    bool ok = true;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+        const double xn = f[d] * P.dt + x[d];          // two roundings (discretizer.py:363)
+        if (x_next) x_next[idx * N + d] = xn;
+        if (xn < P.lb[d] || xn > P.ub[d]) ok = false;  // strict box test (system.py:198-205)
+    }
+    if (x_ok) x_ok[idx] = ok ? 1 : 0;
+    if (G) {
+        double g = 1.0;
+        if (P.cost_id == PDP_COST_QUADRATIC) g = quad_form<N>(P.Q, dx) + __ldg(P.gu + a);
+        if (P.cost_id == PDP_COST_REACH) g = 0.0;
+        if (P.ontarget_check && norm2<N>(dx) < P.EPS) g = 0.0;
+        G[idx] = (ok && P.act_ok[a]) ? g * P.dt : P.INF;
+    }
+}
+

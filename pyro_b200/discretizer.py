@@ -67,6 +67,8 @@ class GridDynamicSystem:
     # -- dense look-up tables, exactly as the reference builds them (discretizer.py:314-402): O(N*A) host loops,
     #    meant for small grids and for LUT mode with systems the fused kernels do not know ----------------------
     def compute_xnext_table(self):
+        if self._device_xnext_table():
+            return
         X, U = self.state_from_node_id, self.input_from_action_id
         self.x_next_table = np.zeros((self.nodes_n, self.actions_n, self.sys.n), dtype=float)
         self.x_next_isok = np.zeros((self.nodes_n, self.actions_n), dtype=bool)
@@ -76,6 +78,30 @@ class GridDynamicSystem:
                 x_next = self.sys.f(x, U[action_id, :]) * self.dt + x
                 self.x_next_table[node_id, action_id, :] = x_next
                 self.x_next_isok[node_id, action_id] = self.sys.isavalidstate(x_next)
+
+    def _device_xnext_table(self):
+        """x_next_table / x_next_isok by pdp_build_tables (one thread per (node, action) pair, the sweep kernels' own
+        arithmetic) when the system is one of the four fused ones and a CUDA device is present; False otherwise — the
+        tables are a host-side product of the reference API, so the reference's Python loop below remains their
+        definition (this is not a sweep path: sweeps never fall back)."""
+        try:
+            from . import _lib, costfunction, problem
+            from .engine import Engine, device_count
+            if device_count() == 0:
+                return False
+            P = problem.extract(self, costfunction.QuadraticCostFunction.from_sys(self.sys))
+            if P.system_id == _lib.PDP_SYS_LUT or self.nodes_n * self.actions_n * self.sys.n * 8 > (8 << 30):
+                return False
+            eng = Engine(P)
+        except (RuntimeError, NotImplementedError, ValueError, OSError):
+            return False
+        try:
+            self.x_next_table, self.x_next_isok, _ = eng.build_tables(G=False)
+        except NotImplementedError:
+            return False
+        finally:
+            eng.close()
+        return True
 
     def compute_action_set_table(self):
         X, U = self.state_from_node_id, self.input_from_action_id

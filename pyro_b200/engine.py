@@ -89,6 +89,17 @@ class Engine:
         self._ck(self.lib.pdp_kernel_info(self.h, buf, 160))
         return buf.value.decode()
 
+    def build_tables(self, node_begin=0, count=None, x_next=True, x_ok=True, G=True):
+        """The reference's dense tables of a node range, built on the device (fused systems): (x_next (K,A,n) or None,
+        x_next_isok (K,A) bool or None, G (K,A) or None)."""
+        count = self.N - node_begin if count is None else count
+        xn = np.empty((count, self.A, self.n)) if x_next else None
+        ok = np.empty((count, self.A), dtype=np.uint8) if x_ok else None
+        Gt = np.empty((count, self.A)) if G else None
+        ptr = lambda a: a.ctypes.data if a is not None else None
+        self._ck(self.lib.pdp_build_tables(self.h, int(node_begin), int(count), ptr(xn), ptr(ok), ptr(Gt)))
+        return xn, (ok.astype(bool) if ok is not None else None), Gt
+
     def set_lut(self, x_next, G):
         x_next = np.ascontiguousarray(x_next, dtype=np.float64)
         G = np.ascontiguousarray(G, dtype=np.float64)

@@ -632,3 +632,26 @@ def test_planner_uses_every_gpu_without_a_launcher(monkeypatch):
     assert np.array_equal(dp.J, J3)
     ctl = dp.get_lookup_table_controller()
     assert ctl.c(np.zeros(4), ctl.rbar).shape == (2,)
+
+
+@pytest.mark.parametrize("name", ["pend_101x101x21", "pend_time_41x61x7", "dpend_example", "twolink_soft", "cartpole_swingup",
+                                  "pend_reach_41x41x3", "cartpole_domaincheck"])
+def test_device_built_lookup_tables_equal_the_reference_tables(name):
+    """The step before the sweep: x_next_table, x_next_isok and G built by pdp_build_tables against the
+    samples of the reference's own tables stored in the fixtures (discretizer.py:342-376, dynamicprogramming.py:517-553),
+    and the mirror grid's lookup=True path, which uses the device builder on a GPU box."""
+    case, gold = CASES[name], load_golden(name)
+    _, grid, cf = build_case(case)
+    eng = Engine(problem.extract(grid, cf, case.get("alpha", 1.0)))
+    x_next, x_ok, G = eng.build_tables()
+    stride = int(gold["table_stride"])
+    assert np.array_equal(x_next[::stride], gold["x_next_sample"])
+    assert np.array_equal(x_ok[::stride], gold["x_next_isok_sample"])
+    assert np.array_equal(G[::stride], gold["G_sample"])
+    lo, cnt = grid.nodes_n // 3, 77                                  # a node range
+    xr, okr, Gr = eng.build_tables(lo, cnt)
+    assert np.array_equal(xr, x_next[lo:lo + cnt]) and np.array_equal(okr, x_ok[lo:lo + cnt]) and np.array_equal(Gr, G[lo:lo + cnt])
+    eng.close()
+    _, lgrid, _ = build_case(case, lookup=True)                      # GridDynamicSystem(..., lookup=True) on the mirror
+    assert np.array_equal(lgrid.x_next_table, x_next) and np.array_equal(lgrid.x_next_isok, x_ok)
+    assert gold["action_isok_sample"].all() and lgrid.action_isok.all()
