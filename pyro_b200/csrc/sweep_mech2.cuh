@@ -33,8 +33,12 @@
 #ifndef SWEEP_THREADS
 #define SWEEP_THREADS 128
 #endif
+// Resident blocks per SM asked of ptxas (register budget), measured on B200 (profiles/r02h_variants.jsonl, ms per sweep
+// cfg3 / cfg4 / DoublePendulum 81^4): 4 blocks (128 registers) 119 / 243 / 384, 5 blocks (96, 40 B spilled) 122 / 249 / 459,
+// 6 blocks (80, ~100 B spilled) 126 / 234 / 466.  The cart-pole kernel is the one that is not yet L1-saturated at four
+// blocks (L1 data pipe 79 %, ncu r02g) and gains from the extra warps; the two-input kernel loses to its spills.
 #ifndef MECH2R_MIN_BLOCKS
-#define MECH2R_MIN_BLOCKS 4
+#define MECH2R_MIN_BLOCKS(SYS) ((SYS) == PDP_SYS_CARTPOLE ? 6 : 4)
 #endif
 
 // make a pointer opaque to the optimiser: ptr[int_index] then compiles to one IMAD.WIDE from a register-resident base
@@ -81,7 +85,7 @@ __device__ __forceinline__ const T* opaque_ptr(const T* p) {
 #define MECH2_CORNER_PTR(i) (b00 + (o + ((((i) >> 2) & 1) ? plane_sz : 0) + (((i) >> 3) ? n1ps : 0) + ((((i) >> 1) & 1) ? N3 : 0)) + ((i) & 1))
 
 template <int SYS, bool ALPHA1>
-__global__ void __launch_bounds__(SWEEP_THREADS, MECH2R_MIN_BLOCKS)
+__global__ void __launch_bounds__(SWEEP_THREADS, MECH2R_MIN_BLOCKS(SYS))
 sweep_mech2_range_kernel(const __grid_constant__ DevProblem P, const double* __restrict__ Jn, double* __restrict__ Jo,
                          long long* __restrict__ pi, unsigned long long* __restrict__ partials, unsigned int* counter,
                          double* __restrict__ stats) {

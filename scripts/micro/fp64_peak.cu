@@ -1,6 +1,6 @@
 // FP64 pipe micro-benchmark (B200, sm_100a): what the sweep kernels can at best issue.
 //   build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scripts/micro/fp64_peak scripts/micro/fp64_peak.cu
-// Prints warp-level FP64 instructions per clock per SM for: independent DFMA chains, DADD chains, DMUL chains,
+// Prints warp-level FP64 instructions per clock per SM (launch duration by CUDA events, SM clock measured in-kernel) for: independent DFMA chains, DADD chains, DMUL chains,
 // DSETP, a DADD/DMUL/DFMA mix with the sweep's proportions, and the same mix with one integer/select
 // instruction interleaved per FP64 instruction.  Time by CUDA events; clock from cudaDevAttrClockRate is
 // not trusted: SM cycles are read with clock64() inside the kernel.
@@ -63,9 +63,14 @@ static void run(const char* name, int blocks_per_sm, int threads, double fp64_pe
     cudaMemcpy(h, ns, blocks * sizeof(long long), cudaMemcpyDeviceToHost);
     double avg_ns = 0; for (int i = 0; i < blocks; ++i) avg_ns += h[i]; avg_ns /= blocks;
     const double warp_inst_per_sm = (double)blocks_per_sm * (threads / 32) * ITERS * fp64_per_iter;
-    printf("%-30s ILP=%d warps/SM=%3d : %.3f FP64 warp-inst/clk/SM (%.1f lanes/clk/SM) | %.3f ms, %.0f clock64 ticks, %.0f ns -> %.3f ticks/ns | %.2f G warp-inst/s/SM\n",
-           name, ILP, blocks_per_sm * threads / 32, warp_inst_per_sm / avg, 32.0 * warp_inst_per_sm / avg, ms, avg, avg_ns, avg / avg_ns,
-           warp_inst_per_sm / avg_ns);
+    // ONE throughput column: all FP64 warp instructions of the launch over the launch's duration (CUDA events) in SM
+    // clocks (clock64 ticks per globaltimer ns, measured inside the kernel).  The per-block clock64 span is printed last
+    // for reference only: blocks need not be co-resident for the whole launch, so it is not a throughput.
+    const double ticks_per_ns = avg / avg_ns;
+    const double launch_clocks = (double)ms * 1e6 * ticks_per_ns;
+    const double rate = warp_inst_per_sm / launch_clocks;
+    printf("%-30s ILP=%d warps/SM=%3d : %.3f FP64 warp-inst/clk/SM (%.1f lanes/clk/SM) | launch %.3f ms = %.0f SM clocks at %.3f GHz | per-block span %.0f clocks\n",
+           name, ILP, blocks_per_sm * threads / 32, rate, 32.0 * rate, ms, launch_clocks, ticks_per_ns, avg);
     cudaFree(out); cudaFree(cyc); cudaFree(ns); delete[] h;
 }
 
