@@ -394,7 +394,8 @@ def run_workload(ctx, args, wl_key, primary):
     stream = torch.cuda.current_stream()
     t_setup = time.perf_counter()
     if world > 1:
-        eng = ShardedEngine(grid, cf, 1.0)
+        # slabs whose boundaries equalise the measured compute time per rank (one calibration sweep, not timed)
+        eng = ShardedEngine(grid, cf, 1.0) if os.environ.get("BENCH_EQUAL_SLABS") else ShardedEngine.balanced(grid, cf, 1.0)
         keng = eng.eng
     else:
         eng = Engine(problem.extract(grid, cf, 1.0))
@@ -569,7 +570,8 @@ def run_workload(ctx, args, wl_key, primary):
     parallelism = "single"
     if world > 1:
         parallelism = f"slab{world} over axis 0/{eng.mode}/{eng.halo}" + ("+overlap" if eng.overlap else "") + \
-                      f", halo {keng.halo_lo}+{keng.halo_hi} planes of {keng.plane * 8 / 1e6:.1f} MB"
+                      f", halo {keng.halo_lo}+{keng.halo_hi} planes of {keng.plane * 8 / 1e6:.1f} MB, slab boundaries {eng.bounds}" + \
+                      (" (rebalanced from measured per-rank compute times)" if getattr(eng, "calibration", {}).get("rebalanced") else " (equal)")
     rec = {
         "metric": "state_action_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": world,
         "steps": steps, "warmup": warmup, "ms_per_step": total_ms / steps,

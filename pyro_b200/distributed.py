@@ -54,6 +54,29 @@ def balanced_slab(rank, world, n_planes):
     return rank * n_planes // world, (rank + 1) * n_planes // world
 
 
+def rebalanced_bounds(bounds, times, min_thick):
+    """New slab boundaries from the measured compute time of each slab (work per plane taken as constant inside a slab):
+    equal cumulative work per rank, every slab at least ``min_thick`` planes.  ``bounds``: W+1 plane indices."""
+    W = len(bounds) - 1
+    n0 = bounds[-1]
+    dens = np.zeros(n0)
+    for r in range(W):
+        if bounds[r + 1] > bounds[r]:
+            dens[bounds[r]:bounds[r + 1]] = max(float(times[r]), 1e-9) / (bounds[r + 1] - bounds[r])
+    cum = np.concatenate([[0.0], np.cumsum(dens)])
+    new = [0]
+    for r in range(1, W):
+        new.append(int(np.searchsorted(cum, cum[-1] * r / W, side="left")))
+    new.append(n0)
+    for r in range(1, W):                   # forward / backward passes: minimum thickness
+        new[r] = max(new[r], new[r - 1] + min_thick)
+    for r in range(W - 1, 0, -1):
+        new[r] = min(new[r], new[r + 1] - min_thick)
+    if any(new[r + 1] - new[r] < min_thick for r in range(W)):
+        return list(bounds)
+    return new
+
+
 class _DevView:
     """Expose a raw device pointer through __cuda_array_interface__ (zero-copy torch view)."""
 
@@ -70,7 +93,7 @@ class ShardedEngine:
     """Same interface as ``engine.Engine`` (sweep / get_J / get_pi / ...), sharded over ranks."""
 
     def __init__(self, grid_sys, cf, alpha=1.0, interpol_method="linear", engine_factory=None, group=None,
-                 mode=None, overlap=True, backend=None, halo=None):
+                 mode=None, overlap=True, backend=None, halo=None, bounds=None):
         import torch
         from . import problem as _problem
         dist = _dist()
@@ -94,11 +117,14 @@ class ShardedEngine:
         # halo mode if every rank's halo lies inside its direct neighbours' slabs
         self.mode = None
         min_thick = n0 // self.world
+        self.bounds = None
         if mode in (None, "halo") and min_thick >= 1:
-            self.begin, self.end = balanced_slab(self.rank, self.world, n0)
+            self.bounds = list(bounds) if bounds is not None else [balanced_slab(r, self.world, n0)[0] for r in range(self.world)] + [n0]
+            self.begin, self.end = self.bounds[self.rank], self.bounds[self.rank + 1]
             self.problem, self.eng = make((self.begin, self.end), 0)
             fused = self.problem.system_id != 0
-            if fused and self.eng.halo_lo <= min_thick and self.eng.halo_hi <= min_thick:
+            thinnest = min(self.bounds[r + 1] - self.bounds[r] for r in range(self.world))
+            if fused and self.eng.halo_lo <= thinnest and self.eng.halo_hi <= thinnest:
                 self.mode = "halo"
             else:
                 if mode == "halo":
@@ -144,6 +170,39 @@ class ShardedEngine:
             self.comm_stream = torch.cuda.Stream()
             self.ev_boundary = torch.cuda.Event()
             self.ev_comm = torch.cuda.Event()
+
+    # ---- work-balanced slabs -----------------------------------------------------------------------------
+    @classmethod
+    def balanced(cls, grid_sys, cf, alpha=1.0, interpol_method="linear", group=None, min_gain=0.02, **kw):
+        """Halo-mode engine whose slab boundaries equalise the MEASURED compute time per rank: nodes whose position rows
+        leave the box cost nothing and are not spread evenly over axis 0 (cfg5 on 8 GPUs: slowest rank 10 % above the
+        mean with equal slabs).  One calibration sweep on equal slabs (from h(x); timing does not depend on J), then the
+        engine is rebuilt on the new boundaries if that promises more than ``min_gain``."""
+        eng = cls(grid_sys, cf, alpha, interpol_method, group=group, **kw)
+        if eng.mode != "halo" or eng.world == 1 or eng.cpu or eng.backend != "native":
+            return eng
+        torch, dist = eng.torch, eng.dist
+        eng.eval_terminal_cost()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eng.eng.sweep_async(); eng.eng.commit_sweep()          # warm-up (first launch of the kernel)
+        torch.cuda.synchronize()
+        a.record(); eng.eng.sweep_async(); b.record(); eng.eng.commit_sweep()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b)], device="cuda", dtype=torch.float64)
+        times = [torch.zeros_like(t) for _ in range(eng.world)]
+        dist.all_gather(times, t, group=group)
+        times = [float(x.item()) for x in times]
+        min_thick = max(eng.halo_lo, eng.halo_hi, 1)
+        new = rebalanced_bounds(eng.bounds, times, min_thick)
+        gain = 1.0 - (sum(times) / eng.world) / max(times)
+        if new == eng.bounds or gain < min_gain:
+            eng.calibration = {"times_ms": times, "bounds": eng.bounds, "rebalanced": False}
+            return eng
+        eng.close()
+        torch.cuda.empty_cache()
+        out = cls(grid_sys, cf, alpha, interpol_method, group=group, bounds=new, **kw)
+        out.calibration = {"times_ms": times, "equal_bounds": eng.bounds, "bounds": new, "rebalanced": True}
+        return out
 
     # ---- views of the engine's buffers ------------------------------------------------------------
     def _wrap(self, token, count, typestr):
@@ -260,7 +319,8 @@ class ShardedEngine:
     def _gather_slabs(self, mine, dtype):
         """All-gather variable-size slabs (padded to the thickest) and return the full (N,) host array."""
         torch, dist = self.torch, self.dist
-        cnt = -(-self.n0 // self.world) * self.plane
+        thickest = max(self.bounds[r + 1] - self.bounds[r] for r in range(self.world)) if self.mode == "halo" else -(-self.n0 // self.world)
+        cnt = thickest * self.plane
         send = torch.zeros(cnt, dtype=dtype, device=mine.device)
         send[:self.slab_nodes] = mine[:self.slab_nodes]
         full = torch.empty(cnt * self.world, dtype=dtype, device=mine.device)
@@ -269,7 +329,7 @@ class ShardedEngine:
         out = np.empty(self.N, dtype=full.dtype)
         for r in range(self.world):
             if self.mode == "halo":
-                b, e = balanced_slab(r, self.world, self.n0)
+                b, e = self.bounds[r], self.bounds[r + 1]
             else:
                 b, e, _ = slab_of(r, self.world, self.n0)
             out[b * self.plane:e * self.plane] = full[r, :(e - b) * self.plane]
