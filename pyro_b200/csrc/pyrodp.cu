@@ -314,6 +314,17 @@ static int select_fused_kernel(pdp_handle* h) {
         if (plane_sz > 0x7fffffffLL / 16 || chunks > 0x7fffffffLL / 16)
             return fail(h, PDP_ENOTSUP, "grid too large for one launch (dims[2]*dims[3] too big)");
         P.chunks = (int)chunks;
+        P.tile_rows = 1;
+        if (h->mech2_mode) {   // range kernel: blocks may be tiles of tile_rows x (128 / tile_rows) nodes (PYRODP_TILE_ROWS, default below)
+            int tr = MECH2_DEFAULT_TILE_ROWS;
+            if (const char* env = getenv("PYRODP_TILE_ROWS")) tr = atoi(env);
+            if (tr != 1 && tr != 2 && tr != 4 && tr != 8 && tr != 16) tr = 1;
+            P.tile_rows = tr;
+            if (tr > 1) {
+                const long long tc = SWEEP_THREADS / tr;
+                P.chunks = (int)(((P.dims[2] + tr - 1) / tr) * ((P.dims[3] + tc - 1) / tc));
+            }
+        }
     }
     if (h->smem_bytes > 227 * 1024) return fail(h, PDP_ENOTSUP, "level/action tables exceed shared memory (227 KB)");
     cudaError_t ce = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);

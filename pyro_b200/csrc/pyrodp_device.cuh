@@ -30,7 +30,7 @@ struct DevProblem {
     long long plane_begin;          // first (i0,i1) pair of this launch = first plane * dims[1] (4-D kernels)
     long long slab_node_begin;      // first node of the handle's slab (origin of slab-local tables, LUT mode)
     // 4-D fused kernels: blocks per (i0,i1) plane; structure of the action table for the range kernel (mech2_plan.h)
-    int chunks, A0, A1, pad1;
+    int chunks, A0, A1, tile_rows;   // tile_rows: range kernel, rows of the (i2,i3) plane per block (1 = 128 consecutive nodes)
     double uv_first, uv_inv_step;
 };
 

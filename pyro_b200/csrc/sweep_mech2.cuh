@@ -50,6 +50,10 @@ __device__ __forceinline__ const T* opaque_ptr(const T* p) {
     return p;
 }
 
+#ifndef MECH2_DEFAULT_TILE_ROWS
+#define MECH2_DEFAULT_TILE_ROWS 1
+#endif
+
 // first out-of-box index bookkeeping: NONE = no INF entry in this node's Q row so far
 #define MECH2_NONE 0x7fffffff
 
@@ -115,15 +119,32 @@ sweep_mech2_range_kernel(const __grid_constant__ DevProblem P, const double* __r
     const long long pl = P.plane_begin + (long long)pl_local;     // (i0,i1) pair, C order
     const int i0 = (int)(pl / N1);
     const int i1 = (int)(pl - (long long)i0 * N1);
-    const int r_raw = (int)(chunk * SWEEP_THREADS + threadIdx.x);  // (i2,i3) within the plane
-    const bool active = r_raw < plane_sz;
-    const int r = min(r_raw, plane_sz - 1);   // lanes past the end of the plane shadow its last node: the action loops are
-                                               // warp-uniform (votes inside), their result is discarded
+    // Nodes of a block: 128 consecutive nodes of the plane (tile_rows == 1), or a tile of tile_rows adjacent i2 rows x
+    // 128/tile_rows columns, one warp-row each: the warps of a block then gather from the same base planes, the same
+    // columns and adjacent k2 rows, i.e. they share L1 lines (ncu: an L1 miss costs extra data-pipe wavefronts).
+    int i2, i3;
+    bool active;
+    if (P.tile_rows > 1) {
+        const int tc = SWEEP_THREADS / P.tile_rows;                 // columns per tile (32: one warp per row; 16 / 8: two / four rows per warp)
+        const unsigned tiles_c = (unsigned)((N3 + tc - 1) / tc);
+        const unsigned tile_r = chunk / tiles_c, tile_c = chunk - tile_r * tiles_c;
+        i2 = (int)tile_r * P.tile_rows + (int)threadIdx.x / tc;
+        i3 = (int)tile_c * tc + (int)threadIdx.x % tc;
+        active = i2 < N2 && i3 < N3;
+    } else {
+        const int r_raw = (int)(chunk * SWEEP_THREADS + threadIdx.x);
+        active = r_raw < plane_sz;
+        const int rr = min(r_raw, plane_sz - 1);
+        i2 = rr / N3;
+        i3 = rr - i2 * N3;
+    }
+    // lanes outside the plane shadow a valid node: the action loops are warp-uniform (votes inside), their result is discarded
+    i2 = min(i2, N2 - 1);
+    i3 = min(i3, N3 - 1);
+    const int r = i2 * N3 + i3;                                   // (i2,i3) within the plane
     const long long node = pl * plane_sz + r;
     const double PINF = __longlong_as_double(0x7ff0000000000000LL);
 
-    const int i2 = r / N3;
-    const int i3 = r - i2 * N3;
     const double q0 = __ldg(P.level[0] + i0), q1 = __ldg(P.level[1] + i1);
     const double dq0 = s_lev2[i2], dq1 = s_lev3[i3];
     const double dt = P.dt;

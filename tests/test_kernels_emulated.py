@@ -222,3 +222,17 @@ def test_emulated_slab_sweeps_need_only_their_halo(name, world):
     assert np.array_equal(J, J_ref) and np.array_equal(pi, pi_ref)
     stats = np.array(stats)
     assert stats[:, 0].max() == st_ref[0] and stats[:, 1].max() == st_ref[1] and stats[:, 2].min() == st_ref[2]
+
+
+@pytest.mark.parametrize("tile_rows", ["1", "4", "16"])
+def test_emulated_range_kernel_block_tiles(monkeypatch, tile_rows):
+    """The 4-D range kernel with blocks shaped as tiles of adjacent i2 rows (PYRODP_TILE_ROWS), ragged planes."""
+    monkeypatch.setenv("PYRODP_TILE_ROWS", tile_rows)
+    for case in (dict(system="CartPole", x_grid_dim=[3, 4, 19, 37], u_grid_dim=[9], xbar=[0.0, float(np.pi), 0.0, 0.0], INF=1000.0),
+                 dict(CASES["dpend_example"], x_grid_dim=[3, 4, 21, 35], u_grid_dim=[5, 7])):
+        _, grid, cf = build_case(case)
+        P = problem.extract(grid, cf, case.get("alpha", 1.0))
+        J0 = np.random.default_rng(3).uniform(0, 300, P.N)
+        Jr, pr = c_oracle.sweep_fused(P, J0)
+        J, pi, st = emu.sweep(P, J0, lanes=1, mech2="range")
+        assert np.array_equal(J, Jr) and np.array_equal(pi, pr) and st[0] == Jr.max()

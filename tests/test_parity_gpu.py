@@ -655,3 +655,26 @@ def test_device_built_lookup_tables_equal_the_reference_tables(name):
     _, lgrid, _ = build_case(case, lookup=True)                      # GridDynamicSystem(..., lookup=True) on the mirror
     assert np.array_equal(lgrid.x_next_table, x_next) and np.array_equal(lgrid.x_next_isok, x_ok)
     assert gold["action_isok_sample"].all() and lgrid.action_isok.all()
+
+
+@pytest.mark.parametrize("tile_rows", ["1", "2", "4", "8", "16"])
+@pytest.mark.parametrize("name,case", [
+    ("cartpole_ragged", dict(system="CartPole", x_grid_dim=[5, 7, 37, 45], u_grid_dim=[21], xbar=[0.0, float(np.pi), 0.0, 0.0], INF=1000.0)),
+    ("dpend_ex_ragged", dict(CASES["dpend_example"], x_grid_dim=[5, 6, 35, 41], u_grid_dim=[9, 11])),
+])
+def test_range_kernel_block_tiles_equal_c_oracle(monkeypatch, name, case, tile_rows):
+    """PYRODP_TILE_ROWS: a block of the range kernel is 128 consecutive nodes (1) or a tile of 2 ... 16 adjacent i2 rows; plane
+    sizes that are no multiple of any tile (ragged last tiles in both directions)."""
+    monkeypatch.setenv("PYRODP_TILE_ROWS", tile_rows)
+    monkeypatch.setenv("PYRODP_LANES", "1")
+    _, grid, cf = build_case(case)
+    P = problem.extract(grid, cf, case.get("alpha", 1.0))
+    eng = Engine(P)
+    assert "range_kernel" in eng.kernel_info
+    J0 = np.random.default_rng(12).uniform(0, 300, P.N)
+    eng.set_J(J0)
+    st = eng.sweep(1)
+    Jr, pr = c_oracle.sweep_fused(P, J0)
+    assert np.array_equal(eng.get_J(), Jr) and np.array_equal(eng.get_pi(), pr), (name, tile_rows)
+    assert st[0, 0] == Jr.max()
+    eng.close()
