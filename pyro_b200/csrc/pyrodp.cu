@@ -289,7 +289,7 @@ static int select_fused_kernel(pdp_handle* h) {
     h->mech2_mode = 0;
     if (P.system_id != PDP_SYS_PENDULUM && G == 1 && h->plan.ok && !h->force_generic && h->force_mech2 != 0) {
         const size_t n2p = (size_t)((P.dims[2] + 1) & ~1), n3p = (size_t)((P.dims[3] + 1) & ~1);
-        const size_t smem = (2 * n2p + 2 * n3p + 3 * A) * sizeof(double) + 16;
+        const size_t smem = (2 * n2p + 2 * n3p + (size_t)((h->plan.A0 + 1) & ~1) + (size_t)((h->plan.A1 + 1) & ~1) + A) * sizeof(double) + 16;
         const bool offsets_fit = 2LL * P.dims[1] * P.dims[2] * P.dims[3] < 0x7fffffffLL;   // 32-bit corner offsets of the range kernel
         if (smem <= 200 * 1024 && offsets_fit) {
             if (P.system_id == PDP_SYS_TWOLINK) k = a1 ? sweep_mech2_range_kernel<PDP_SYS_TWOLINK, true> : sweep_mech2_range_kernel<PDP_SYS_TWOLINK, false>;
@@ -316,7 +316,7 @@ static int select_fused_kernel(pdp_handle* h) {
         P.chunks = (int)chunks;
         P.tile_rows = 1;
         if (h->mech2_mode) {   // range kernel: blocks may be tiles of tile_rows x (128 / tile_rows) nodes (PYRODP_TILE_ROWS, default below)
-            int tr = MECH2_DEFAULT_TILE_ROWS;
+            int tr = MECH2_DEFAULT_TILE_ROWS(P.system_id);
             if (const char* env = getenv("PYRODP_TILE_ROWS")) tr = atoi(env);
             if (tr != 1 && tr != 2 && tr != 4 && tr != 8 && tr != 16) tr = 1;
             P.tile_rows = tr;
@@ -329,6 +329,17 @@ static int select_fused_kernel(pdp_handle* h) {
     if (h->smem_bytes > 227 * 1024) return fail(h, PDP_ENOTSUP, "level/action tables exceed shared memory (227 KB)");
     cudaError_t ce = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
     if (ce != cudaSuccess) return fail(h, PDP_ECUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
+    // Shared memory is carved out of the 256 KB L1: ask for no more than the resident blocks need, the rest stays cache
+    // (the 4-D kernels are bound by L1 miss fills).  A hint; the driver rounds it up to a supported split.
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k, SWEEP_THREADS, h->smem_bytes) == cudaSuccess && occ > 0) {
+        const double need = (double)occ * (double)(h->smem_bytes + 1024);   // + the per-block reservation
+        int pct = (int)(need / (228.0 * 1024.0) * 100.0) + 1;
+        pct = std::min(std::max(pct, 1), 100);
+        if (cudaFuncSetAttribute((const void*)k, cudaFuncAttributePreferredSharedMemoryCarveout, pct) != cudaSuccess) cudaGetLastError();
+    } else {
+        cudaGetLastError();
+    }
     return PDP_OK;
 }
 

@@ -50,8 +50,14 @@ __device__ __forceinline__ const T* opaque_ptr(const T* p) {
     return p;
 }
 
+// Block shape (rows of the (i2,i3) plane per 128-node block), measured on B200 (profiles/r02k_tiles.jsonl, ms per sweep
+// cfg3 / cfg4 / DoublePendulum 81^4 / cfg5): 1 row 113.8 / 236.2 / 373.9 / 17 079; 4 rows x 32 columns 113.1 / 245.2 / 358.6 / 14 670;
+// 8 x 16: 109.2 / 238.1 / 337.1 / 14 159; 16 x 8: 109.4 / 240.9 / 343.5.  Adjacent i2 rows gather from the same base planes and
+// columns and from k2 rows that differ by about one, so a tile's warps share L1 lines (an L1 miss costs extra data-pipe
+// wavefronts, which is what binds the kernel); the cart-pole's hit rate is 91 % already and it only pays the ragged tiles.
+// (256-thread blocks — 16 x 16 and 8 x 32 tiles — measured slower: r02l, DoublePendulum 81^4 363 / 378 ms against 351.)
 #ifndef MECH2_DEFAULT_TILE_ROWS
-#define MECH2_DEFAULT_TILE_ROWS 1
+#define MECH2_DEFAULT_TILE_ROWS(SYS) ((SYS) == PDP_SYS_TWOLINK ? 8 : 1)
 #endif
 
 // first out-of-box index bookkeeping: NONE = no INF entry in this node's Q row so far
@@ -101,14 +107,17 @@ sweep_mech2_range_kernel(const __grid_constant__ DevProblem P, const double* __r
     double* s_rinv2 = s_lev2 + N2p;              // [N2p] correctly rounded 1/(lev[k+1]-lev[k])
     double* s_lev3 = s_rinv2 + N2p;              // [N3p]
     double* s_rinv3 = s_lev3 + N3p;              // [N3p]
-    double2* s_act = (double2*)(s_rinv3 + N3p);  // [A] {B.u[0], B.u[1]}
-    double* s_gu = (double*)(s_act + A);         // [A] du'R du
+    // The action table is separable (mech2_plan.h): row CV of B.u is a function of the inner index, row 1-CV of the outer
+    // one — A0 + A1 doubles instead of 2A (15 KB per block at 31 x 31 actions: shared memory is carved out of the L1, and
+    // what binds this kernel is L1 miss fills).  du'R du stays a table per action.
+    double* s_buv = s_rinv3 + N3p;               // [A1] B.u[CV] along the inner index
+    double* s_buo = s_buv + ((A1 + 1) & ~1);     // [A0] B.u[1-CV] along the outer index
+    double* s_gu = s_buo + ((A0 + 1) & ~1);      // [A] du'R du
     for (int i = threadIdx.x; i < N2; i += blockDim.x) { s_lev2[i] = __ldg(P.level[2] + i); s_rinv2[i] = __ldg(P.rinv[2] + i); }
     for (int i = threadIdx.x; i < N3; i += blockDim.x) { s_lev3[i] = __ldg(P.level[3] + i); s_rinv3[i] = __ldg(P.rinv[3] + i); }
-    for (int i = threadIdx.x; i < A; i += blockDim.x) {
-        s_act[i] = make_double2(__ldg(P.bu + 2 * i), __ldg(P.bu + 2 * i + 1));
-        s_gu[i] = __ldg(P.gu + i);
-    }
+    for (int i = threadIdx.x; i < A1; i += blockDim.x) s_buv[i] = __ldg(P.bu + 2 * i + CV);
+    for (int i = threadIdx.x; i < A0; i += blockDim.x) s_buo[i] = __ldg(P.bu + 2 * (i * A1) + (1 - CV));
+    for (int i = threadIdx.x; i < A; i += blockDim.x) s_gu[i] = __ldg(P.gu + i);
     __syncthreads();
 
     // block -> ((i0,i1) plane, chunk of the (i2,i3) plane), chunk fastest
@@ -233,10 +242,10 @@ sweep_mech2_range_kernel(const __grid_constant__ DevProblem P, const double* __r
         const int base = a0 * A1;
         // the outer residual: row (1-CV) of B u - C dq - g - d, left to right (mechanical.py:231).  For the
         // cart-pole g[0], d[0], d[1] are literal zeros (cartpole.py:415-437) and x - 0.0 == x bit for bit.
-        const double2 bu_o = s_act[base];
+        const double bu_o = s_buo[a0];
         double r_o;
-        if (SYS == PDP_SYS_TWOLINK) r_o = ((bu_o.x - cd0) - g0) - d0;     // CV = 1: outer row 0
-        else r_o = (bu_o.y - cd1) - g1;                                  // CV = 0: outer row 1 (B.u[1] = +-0)
+        if (SYS == PDP_SYS_TWOLINK) r_o = ((bu_o - cd0) - g0) - d0;       // CV = 1: outer row 0
+        else r_o = (bu_o - cd1) - g1;                                    // CV = 0: outer row 1 (B.u[1] = +-0)
         int lo = A1, hi = 0;    // a lane that is not live has an empty bracket
         if (live) {
             const double t2 = HA2 * r_o, t3 = HA3 * r_o;
@@ -264,11 +273,11 @@ sweep_mech2_range_kernel(const __grid_constant__ DevProblem P, const double* __r
             const int a1 = start + it;
             if (a1 < lo || a1 >= hi) continue;  // outside this lane's bracket: Q = INF, already accounted for
             const int a = base + a1;
-            const double2 bu = s_act[a];        // a broadcast when the warp is in step
+            const double bu_v = s_buv[a1];      // a broadcast when the warp is in step
             const double gua = s_gu[a];
             double r0, r1;
-            if (SYS == PDP_SYS_TWOLINK) { r0 = r_o; r1 = ((bu.y - cd1) - g1) - d1; }
-            else { r0 = bu.x - cd0; r1 = r_o; }
+            if (SYS == PDP_SYS_TWOLINK) { r0 = r_o; r1 = ((bu_v - cd1) - g1) - d1; }
+            else { r0 = bu_v - cd0; r1 = r_o; }
             const double ddq0 = mv2(H00, H01, r0, r1);
             const double ddq1 = mv2(H10, H11, r0, r1);
             const double x2 = ddq0 * dt + dq0;

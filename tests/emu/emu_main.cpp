@@ -237,15 +237,15 @@ extern "C" int emu_sweep_planes(const pdp_problem* p, const double* J_next, doub
             grid = {(unsigned)((p1 - p0) * P.dims[1] * P.chunks), 1, 1};
             P.tile_rows = 1;
             if (G == 1 && H.plan.ok && force_generic != 1) {   // pyrodp.cu select_fused_kernel
-                int tr = MECH2_DEFAULT_TILE_ROWS;
+                int tr = MECH2_DEFAULT_TILE_ROWS(P.system_id);
                 if (const char* env = getenv("PYRODP_TILE_ROWS")) tr = atoi(env);
                 if (tr != 1 && tr != 2 && tr != 4 && tr != 8 && tr != 16) tr = 1;
                 P.tile_rows = tr;
                 if (tr > 1) {
                     const int tc = SWEEP_THREADS / tr;
                     P.chunks = ((P.dims[2] + tr - 1) / tr) * ((P.dims[3] + tc - 1) / tc);
-                    grid = {(unsigned)((p1 - p0) * P.dims[1] * P.chunks), 1, 1};
                 }
+                grid = {(unsigned)((p1 - p0) * P.dims[1] * P.chunks), 1, 1};
                 if (P.system_id == PDP_SYS_TWOLINK) k = a1 ? sweep_mech2_range_kernel<PDP_SYS_TWOLINK, true> : sweep_mech2_range_kernel<PDP_SYS_TWOLINK, false>;
                 else k = a1 ? sweep_mech2_range_kernel<PDP_SYS_CARTPOLE, true> : sweep_mech2_range_kernel<PDP_SYS_CARTPOLE, false>;
             }
