@@ -146,6 +146,7 @@ struct pdp_handle {
     int policy_blocks = 0;        // one resident wave of sweep_policy_kernel blocks
     bool pend_mono = false;       // pendulum: x_next[1] is non-decreasing along the action list (see sweep_fused.cuh, MONO)
     bool force_generic = false;   // test hook (PYRODP_GENERIC=1): use the order-agnostic action loop anyway
+    int pend_loop = 2;            // MONO variant of the pendulum kernel: 2 = loop nest (shipped), 1 = round 1's pair loop (PYRODP_PEND_LOOP=1, A/B)
     int mech2_mode = 0;           // 4-D fused systems: 0 order-agnostic kernel, 1 range-skipping kernel
     int force_mech2 = -1;         // test / A-B hook (PYRODP_MECH2=generic|range)
     int test_interior_delay_us = 0;   // test hook (PYRODP_TEST_INTERIOR_DELAY_US): spin before the interior planes of a sharded sweep
@@ -253,11 +254,12 @@ static int expected_tab_len(const pdp_problem* p, int t, long long* len) {
 typedef void (*fused_kernel_t)(const DevProblem, const double*, double*, long long*, unsigned long long*, unsigned int*, double*);
 
 template <int G, bool A1>
-static fused_kernel_t fused_for(int system_id, bool nodamp, bool mono) {
+static fused_kernel_t fused_for(int system_id, bool nodamp, int mono) {
     switch (system_id) {
         case PDP_SYS_PENDULUM:
-            if (mono) return nodamp ? sweep_pendulum_kernel<G, A1, true, true> : sweep_pendulum_kernel<G, A1, false, true>;
-            return nodamp ? sweep_pendulum_kernel<G, A1, true, false> : sweep_pendulum_kernel<G, A1, false, false>;
+            if (mono == 2) return nodamp ? sweep_pendulum_kernel<G, A1, true, 2> : sweep_pendulum_kernel<G, A1, false, 2>;
+            if (mono == 1) return nodamp ? sweep_pendulum_kernel<G, A1, true, 1> : sweep_pendulum_kernel<G, A1, false, 1>;
+            return nodamp ? sweep_pendulum_kernel<G, A1, true, 0> : sweep_pendulum_kernel<G, A1, false, 0>;
         case PDP_SYS_TWOLINK: return sweep_mech2_kernel<PDP_SYS_TWOLINK, G, A1>;
         case PDP_SYS_CARTPOLE: return sweep_mech2_kernel<PDP_SYS_CARTPOLE, G, A1>;
     }
@@ -279,7 +281,7 @@ static int select_fused_kernel(pdp_handle* h) {
     const bool a1 = P.alpha_is_one != 0;
     fused_kernel_t k = nullptr;
     const bool nd = (P.system_id == PDP_SYS_PENDULUM) && P.par[1] == 0.0;  // d1 == 0: no damping term
-    const bool mono = h->pend_mono && !h->force_generic;
+    const int mono = (h->pend_mono && !h->force_generic) ? h->pend_loop : 0;
     if (G == 1) k = a1 ? fused_for<1, true>(P.system_id, nd, mono) : fused_for<1, false>(P.system_id, nd, mono);
     else if (G == 4) k = a1 ? fused_for<4, true>(P.system_id, nd, mono) : fused_for<4, false>(P.system_id, nd, mono);
     else k = a1 ? fused_for<16, true>(P.system_id, nd, mono) : fused_for<16, false>(P.system_id, nd, mono);
@@ -302,7 +304,7 @@ static int select_fused_kernel(pdp_handle* h) {
     h->fused = (void*)k;
     if (P.system_id == PDP_SYS_PENDULUM) {
         const size_t n1p = (size_t)((P.dims[1] + 1) & ~1);
-        h->smem_bytes = (2 * n1p + 2 * (A + 2 * (size_t)G)) * sizeof(double) + 16;  // {level, 1/step} records + padded action records
+        h->smem_bytes = (2 * n1p + 2 * (A + 4 * (size_t)G)) * sizeof(double) + 16;  // {level, 1/step} records + padded action records
         if (h->N > 0x7fffffffLL) return fail(h, PDP_ENOTSUP, "2-D grids are limited to 2^31-1 nodes");
         if (((long long)P.dims[1] * G + SWEEP_THREADS - 1) / SWEEP_THREADS > 65535)
             return fail(h, PDP_ENOTSUP, "grid too large for one launch (dims[1] too big)");
@@ -431,6 +433,7 @@ extern "C" int pdp_create(const pdp_problem* p, pdp_handle** out) {
     if (cudaGetDevice(&h->device) != cudaSuccess) { g_err = "cudaGetDevice failed"; return bail(PDP_ECUDA); }
     if (const char* env = getenv("PYRODP_LANES")) h->force_lanes = atoi(env);
     if (const char* env = getenv("PYRODP_GENERIC")) h->force_generic = atoi(env) != 0;
+    if (const char* env = getenv("PYRODP_PEND_LOOP")) h->pend_loop = (atoi(env) == 1) ? 1 : 2;
     if (const char* env = getenv("PYRODP_TEST_INTERIOR_DELAY_US")) h->test_interior_delay_us = atoi(env);
     if (const char* env = getenv("PYRODP_MECH2"))
         h->force_mech2 = !strcmp(env, "generic") ? 0 : !strcmp(env, "range") ? 1 : -1;
@@ -703,7 +706,7 @@ extern "C" int pdp_kernel_info(const pdp_handle* h, char* out, int32_t len) {
     std::string name;
     const DevProblem& P = h->P;
     if (P.system_id == PDP_SYS_LUT) name = P.A == 1 ? "sweep_policy_kernel" : "sweep_lut_kernel";
-    else if (P.system_id == PDP_SYS_PENDULUM) name = std::string("sweep_pendulum_kernel<") + (h->pend_mono && !h->force_generic ? "mono" : "generic") + ">";
+    else if (P.system_id == PDP_SYS_PENDULUM) name = std::string("sweep_pendulum_kernel<") + (h->pend_mono && !h->force_generic ? (h->pend_loop == 2 ? "mono, loop nest" : "mono, pair loop") : "generic") + ">";
     else {
         const char* sys = P.system_id == PDP_SYS_TWOLINK ? "TWOLINK" : "CARTPOLE";
         if (h->mech2_mode) name = std::string("sweep_mech2_range_kernel<") + sys + ">";

@@ -76,6 +76,29 @@ __device__ __forceinline__ double pinned(double x) {
     return __longlong_as_double(__double_as_longlong(x) | (long long)blockIdx.z);
 }
 
+// Shared-memory record reads of the pendulum action loop through a 32-bit shared-window address that lives in a
+// register: ptxas otherwise re-derives "window base + dynamic offset + 16*a" (eight integer / uniform-datapath
+// instructions) on every pass.  The CPU emulation (tests/emu) has no address spaces: there the address is the pointer.
+#ifdef __CUDACC__
+typedef unsigned smem_addr_t;
+__device__ __forceinline__ smem_addr_t smem_addr_of(const void* p) {
+    smem_addr_t a = (smem_addr_t)__cvta_generic_to_shared(p);
+    asm volatile("" : "+r"(a));
+    return a;
+}
+template <int BYTES>
+__device__ __forceinline__ double2 lds_double2(smem_addr_t a) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(a), "n"(BYTES) : "memory");
+    return v;
+}
+#else
+typedef uintptr_t smem_addr_t;
+static inline smem_addr_t smem_addr_of(const void* p) { return (smem_addr_t)p; }
+template <int BYTES>
+static inline double2 lds_double2(smem_addr_t a) { return *(const double2*)(a + BYTES); }
+#endif
+
 // ---- shared-memory staging of the small tables -------------------------------------------------
 __device__ __forceinline__ void stage(double* dst, const double* __restrict__ src, int n) {
     for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldg(src + i);
@@ -103,23 +126,31 @@ __device__ __forceinline__ void stage(double* dst, const double* __restrict__ sr
 // inv(H) > 0, dt > 0, every action allowed — the linspace input grid of a pendulum): then lo <= x
 // holds by induction, one compare (x < hi) on the later action of a pair covers both, the cell only
 // ever moves up, and a lane whose x_next passed the upper bound is finished.
-template <int G, bool ALPHA1, bool NODAMP, bool MONO>
-__global__ void __launch_bounds__(SWEEP_THREADS)
+#ifndef PEND_MIN_BLOCKS
+#define PEND_MIN_BLOCKS 8
+#endif
+template <int G, bool ALPHA1, bool NODAMP, int MONO>
+__global__ void __launch_bounds__(SWEEP_THREADS, (MONO == 2) ? PEND_MIN_BLOCKS : 0)
 sweep_pendulum_kernel(const __grid_constant__ DevProblem P, const double* __restrict__ Jn, double* __restrict__ Jo,
                       long long* __restrict__ pi, unsigned long long* __restrict__ partials, unsigned int* counter,
                       double* __restrict__ stats) {
     extern __shared__ __align__(16) double smem[];
     const int N0 = P.dims[0], N1 = P.dims[1], A = P.A;
-    double2* s_cell = (double2*)smem;   // [N1] {lev[k], 1/(lev[k+1]-lev[k])}: one LDS.128 per cell change
-    double2* s_act = s_cell + N1;       // [A_pad] {t[a] (NaN when isavalidinput fails), du'R du}; the padding repeats
-                                        // the last action: an equal Q never beats an earlier index
+    // [N1] MONO < 2: {lev[k], 1/(lev[k+1]-lev[k])}; MONO == 2: {1/(lev[k]-lev[k-1]), lev[k]}, so that entry k+1 holds
+    // {1/step, upper level} of cell k.  Either way one LDS.128 per cell change.
+    double2* s_cell = (double2*)smem;
+    double2* s_act = s_cell + N1;       // [A_pad (+ 2G, MONO == 2)] {t[a] (NaN when isavalidinput fails), du'R du}; the
+                                        // padding repeats the last action: an equal Q never beats an earlier index
     const int A_pad = ((A + 2 * G - 1) / (2 * G)) * (2 * G);
+    const int A_stage = (MONO == 2) ? A_pad + 2 * G : A_pad;   // the loop nest may run one pair past A_pad
 
     const int i0 = (int)(P.plane_begin + (long long)blockIdx.x);  // row = axis-0 plane
     const double q = __ldg(P.level[0] + i0);
     const double grav = __ldg(P.tab[0] + i0);    // g(q) (pendulum.py:126-137)
-    for (int i = threadIdx.x; i < N1; i += blockDim.x) s_cell[i] = make_double2(__ldg(P.level[1] + i), __ldg(P.rinv[1] + i));
-    for (int i = threadIdx.x; i < A_pad; i += blockDim.x) {
+    for (int i = threadIdx.x; i < N1; i += blockDim.x)
+        s_cell[i] = (MONO == 2) ? make_double2(i > 0 ? __ldg(P.rinv[1] + i - 1) : 0.0, __ldg(P.level[1] + i))
+                                : make_double2(__ldg(P.level[1] + i), __ldg(P.rinv[1] + i));
+    for (int i = threadIdx.x; i < A_stage; i += blockDim.x) {
         const int a = min(i, A - 1);
         // ddq = inv(H) . (B u - C dq - g - d), C = 0 (mechanical.py:222-234)
         double t = __ldg(P.bu + a) - grav;
@@ -134,7 +165,7 @@ sweep_pendulum_kernel(const __grid_constant__ DevProblem P, const double* __rest
     const long long node = (long long)i0 * N1 + min(i1, N1 - 1);
     const double PINF = __longlong_as_double(0x7ff0000000000000LL);
     const double dt = pinned(P.dt);
-    const double dq_node = s_cell[min(i1, N1 - 1)].x;
+    const double dq_node = (MONO == 2) ? s_cell[min(i1, N1 - 1)].y : s_cell[min(i1, N1 - 1)].x;
 
     // position row of x_next: f[0]*dt + x[0] = dq*dt + q (two roundings, discretizer.py:363)
     const double xn0 = dq_node * dt + q;
@@ -170,7 +201,7 @@ sweep_pendulum_kernel(const __grid_constant__ DevProblem P, const double* __rest
     double p00 = 0.0, p01 = 0.0, p10 = 0.0, p11 = 0.0;
     double best = PINF;
     int besta = 0x7fffffff;
-    if constexpr (MONO) {
+    if constexpr (MONO == 1) {
         // Two actions per iteration under one compare and one warp vote.  evalq = evaluate_linear_2d in
         // its value-first association on the cached products, Q = g*dt + alpha*J
         // (dynamicprogramming.py:223): 15 FP64 issues.
@@ -238,6 +269,123 @@ sweep_pendulum_kernel(const __grid_constant__ DevProblem P, const double* __rest
             if (QA < best) { best = QA; besta = a; }   // strict <, in action order: first index wins (np.argmin)
             if (QB < best) { best = QB; besta = b; }
         }
+        if (besta >= A && besta != 0x7fffffff) besta = A - 1;   // a padded copy of the last action
+    } else if constexpr (MONO == 2) {
+        // Loop nest.  The inner loop runs the pairs of actions the cached cell still covers for EVERY lane of the warp
+        // (one compare on the later action of a pair and one vote per pair, the cell state loop-invariant, two pairs per
+        // pass): 35 FP64 + 11.5 other instructions per pair.  The outer loop handles the pair at which some lane leaves
+        // its cell.  ncu r01K had counted 18.6 non-FP64 instructions per eval for the MONO = 1 loop, half of them on the
+        // cell changes (one pair in five at cfg 2) and 3 per eval re-deriving the shared-memory address of the action
+        // record; the static count of this loop is 5.75 per eval on the common path.
+        double gxv = gx;
+        auto evalq = [&](double x, double gu) {
+            const double y1 = exact_div(x - lo, den, rinv);
+            const double omy1 = 1.0 - y1;
+            double Jx = p00 * omy1;
+            Jx = Jx + p01 * y1;
+            Jx = Jx + p10 * omy1;
+            Jx = Jx + p11 * y1;
+            return (gxv + gu) * dt_cost + (ALPHA1 ? Jx : alpha * Jx);
+        };
+        // x reached the top of the cached cell (or there is none yet).  Common case (nine cell changes in ten at
+        // cfg 2, and the lanes of a row change together): x lies in the NEXT cell — one LDS.128 brings its upper
+        // level and 1/step, its lower corner products are the old upper ones (the same two factors, so the same
+        // bits), two gathers bring the new upper pair.  Anything else: isavalidstate (system.py:198-205), then
+        // walk the level table upwards — the interval scipy's search returns — and gather all four corners.
+        const smem_addr_t cell0 = smem_addr_of(s_cell);
+        auto advance = [&](double x) -> bool {
+            if ((unsigned)c < (unsigned)(N1 - 2)) {
+                const double2 nx = lds_double2<32>(cell0 + 16u * (unsigned)c);   // s_cell[c + 2] = {1/step, upper level} of cell c+1
+                if (x < nx.y) {
+                    ++c; lo = hi; hi = nx.y; rinv = nx.x; den = hi - lo;
+                    p00 = p01; p10 = p11;
+                    p01 = __ldg(row0 + c + 1) * omy0;
+                    p11 = __ldg(row1 + c + 1) * y0;
+                    return false;
+                }
+            }
+            const double lb1 = P.lb[1], ub1 = P.ub[1];
+            if (!(x <= ub1)) {
+                // above the box, and so is every later action: park the lane on an all-covering cell
+                // with an infinite state cost, so that its Q (inf, or NaN when dt_cost is 0) never wins again
+                hi = PINF;
+                gxv = PINF;
+                return true;
+            }
+            if (x < lb1) return true;   // still below the box
+            int k;
+            double l, h;
+            if (c < 0) {   // first cell of this node: arithmetic guess, the table decides
+                k = min(max((int)((x - lb1) * P.inv_step[1]), 0), N1 - 2);
+                l = s_cell[k].y; h = s_cell[k + 1].y;
+                while (x < l && k > 0) { --k; h = l; l = s_cell[k].y; }
+            } else {
+                k = min(c + 1, N1 - 2);
+                l = s_cell[k].y; h = s_cell[k + 1].y;
+            }
+            while (x >= h && k < N1 - 2) { ++k; l = h; h = s_cell[k + 1].y; }
+            c = k; lo = l; hi = h; den = h - l; rinv = s_cell[k + 1].x;
+            const double* __restrict__ r0 = row0 + k;
+            const double* __restrict__ r1 = row1 + k;
+            p00 = __ldg(r0) * omy0; p01 = __ldg(r0 + 1) * omy0;
+            p10 = __ldg(r1) * y0;   p11 = __ldg(r1 + 1) * y0;
+            return false;
+        };
+        auto slow = [&](double x, double gu) {
+            bool oob = false;
+            if (!(x < hi)) oob = advance(x);
+            const double Q = evalq(x, gu);
+            return oob ? INF : Q;
+        };
+        hi = live ? -PINF : PINF;   // live lanes: no cell yet, the first action locates it
+        // Loop nest: the inner loop runs the pairs the cached cell still covers for every lane of the warp (the cell
+        // state is loop-invariant there); the outer loop handles the pair at which some lane leaves its cell.
+        // The action records are walked by ADDRESS (one add per pair; the argmin remembers the address of its record).
+        const smem_addr_t act0 = smem_addr_of(s_act);
+        const smem_addr_t pend = act0 + 16u * (unsigned)A_pad;
+        smem_addr_t pa = act0 + 16u * (unsigned)g, bestp = 0;
+        while (pa < pend) {
+            bool leave;
+            // two pairs per pass, the end test after the second: a pass may run one pair into the padding (copies of
+            // the last action: an equal Q never replaces an earlier index)
+            do {
+                {
+                    const double2 actA = lds_double2<0>(pa), actB = lds_double2<16 * G>(pa);
+                    const double xA = NODAMP ? (actA.x + dq) : ((Hinv * (actA.x - damp)) * dt + dq);
+                    const double xB = NODAMP ? (actB.x + dq) : ((Hinv * (actB.x - damp)) * dt + dq);
+                    leave = __any_sync(0xffffffffu, !(xB < hi));   // xA <= xB: one compare covers the pair
+                    if (leave) break;
+                    const double QA = evalq(xA, actA.y);
+                    const double QB = evalq(xB, actB.y);
+                    if (QA < best) { best = QA; bestp = pa; }   // strict <, in action order: first index wins (np.argmin)
+                    if (QB < best) { best = QB; bestp = pa + 16 * G; }
+                }
+                {
+                    const double2 actA = lds_double2<32 * G>(pa), actB = lds_double2<48 * G>(pa);
+                    const double xA = NODAMP ? (actA.x + dq) : ((Hinv * (actA.x - damp)) * dt + dq);
+                    const double xB = NODAMP ? (actB.x + dq) : ((Hinv * (actB.x - damp)) * dt + dq);
+                    leave = __any_sync(0xffffffffu, !(xB < hi));
+                    if (leave) { pa += 32 * G; break; }
+                    const double QA = evalq(xA, actA.y);
+                    const double QB = evalq(xB, actB.y);
+                    if (QA < best) { best = QA; bestp = pa + 32 * G; }
+                    if (QB < best) { best = QB; bestp = pa + 48 * G; }
+                }
+                pa += 64 * G;
+            } while (pa < pend);
+            if (!leave) break;
+            {
+                const double2 actA = lds_double2<0>(pa), actB = lds_double2<16 * G>(pa);
+                const double xA = NODAMP ? (actA.x + dq) : ((Hinv * (actA.x - damp)) * dt + dq);
+                const double xB = NODAMP ? (actB.x + dq) : ((Hinv * (actB.x - damp)) * dt + dq);
+                const double QA = slow(xA, actA.y);
+                const double QB = slow(xB, actB.y);
+                if (QA < best) { best = QA; bestp = pa; }
+                if (QB < best) { best = QB; bestp = pa + 16 * G; }
+                pa += 32 * G;
+            }
+        }
+        if (bestp) besta = (int)((bestp - act0) >> 4);
         if (besta >= A && besta != 0x7fffffff) besta = A - 1;   // a padded copy of the last action
     } else {
         const int A_up = (G > 1) ? ((A + G - 1) / G) * G : A;  // same trip count for every lane of the warp

@@ -38,8 +38,8 @@ MECH2_MODES = {None: 0, "generic": 1, "range": 0}
 
 def _mode(force_generic, mech2):
     """Kernel selection code of emu_sweep*: 0 = as the library selects (the 4-D range kernel for one lane per node when the
-    action table allows it), 1 = the order-agnostic kernels."""
-    return 1 if force_generic else MECH2_MODES[mech2]
+    action table allows it), 1 = the order-agnostic kernels, 2 = round 1's pendulum pair loop (PYRODP_PEND_LOOP=1)."""
+    return int(force_generic) if force_generic else MECH2_MODES[mech2]
 
 
 def sweep(problem, J_next, lanes=1, force_generic=False, mech2=None):

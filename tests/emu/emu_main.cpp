@@ -135,11 +135,12 @@ extern "C" long long emu_mech2_evals(int reset) { long long v = mech2_evals_done
 typedef void (*fused_kernel_t)(const DevProblem, const double*, double*, long long*, unsigned long long*, unsigned int*, double*);
 
 template <int G, bool A1>
-static fused_kernel_t fused_for(int system_id, bool nodamp, bool mono) {
+static fused_kernel_t fused_for(int system_id, bool nodamp, int mono) {
     switch (system_id) {
         case PDP_SYS_PENDULUM:
-            if (mono) return nodamp ? sweep_pendulum_kernel<G, A1, true, true> : sweep_pendulum_kernel<G, A1, false, true>;
-            return nodamp ? sweep_pendulum_kernel<G, A1, true, false> : sweep_pendulum_kernel<G, A1, false, false>;
+            if (mono == 2) return nodamp ? sweep_pendulum_kernel<G, A1, true, 2> : sweep_pendulum_kernel<G, A1, false, 2>;
+            if (mono == 1) return nodamp ? sweep_pendulum_kernel<G, A1, true, 1> : sweep_pendulum_kernel<G, A1, false, 1>;
+            return nodamp ? sweep_pendulum_kernel<G, A1, true, 0> : sweep_pendulum_kernel<G, A1, false, 0>;
         case PDP_SYS_TWOLINK: return sweep_mech2_kernel<PDP_SYS_TWOLINK, G, A1>;
         case PDP_SYS_CARTPOLE: return sweep_mech2_kernel<PDP_SYS_CARTPOLE, G, A1>;
     }
@@ -217,8 +218,8 @@ extern "C" int emu_sweep_planes(const pdp_problem* p, const double* J_next, doub
         DevProblem& P = H.P;
         const int G = lanes;
         const bool a1 = P.alpha_is_one != 0, nd = (P.system_id == PDP_SYS_PENDULUM) && P.par[1] == 0.0;
-        // force_generic: 0 = what the library selects, 1 = order-agnostic kernels
-        const bool mono = H.mono && force_generic != 1;
+        // force_generic: 0 = what the library selects, 1 = order-agnostic kernels, 2 = round 1's pendulum pair loop (PYRODP_PEND_LOOP=1)
+        const int mono = (H.mono && force_generic != 1) ? (force_generic == 2 ? 1 : 2) : 0;
         fused_kernel_t k = nullptr;
         if (G == 1) k = a1 ? fused_for<1, true>(P.system_id, nd, mono) : fused_for<1, false>(P.system_id, nd, mono);
         else if (G == 4) k = a1 ? fused_for<4, true>(P.system_id, nd, mono) : fused_for<4, false>(P.system_id, nd, mono);

@@ -50,6 +50,45 @@ def test_emulated_order_agnostic_pendulum_loop(name, lanes):
     assert np.array_equal(J, gold[f"J_{k}"]) and np.array_equal(pi, gold[f"pi_{k}"])
 
 
+@pytest.mark.parametrize("lanes", [1, 4, 16])
+@pytest.mark.parametrize("name", ["pend_51x51x11", "pend_time_41x61x7", "pend_reach_41x41x3"])
+def test_emulated_round1_pair_loop_of_the_pendulum_kernel(name, lanes):
+    """PYRODP_PEND_LOOP=1 (kept for A/B): the pair loop the loop nest replaced."""
+    case, gold = CASES[name], load_golden(name)
+    _, grid, cf = build_case(case)
+    P = problem.extract(grid, cf, case.get("alpha", 1.0))
+    k = case["snapshots"][0]
+    J, pi = run_sweeps(P, gold["J0"], k, lanes, generic=2)
+    assert np.array_equal(J, gold[f"J_{k}"]) and np.array_equal(pi, gold[f"pi_{k}"])
+
+
+@pytest.mark.parametrize("lanes", [1, 4, 16])
+@pytest.mark.parametrize("shape", [
+    ([19, 260], [1]),      # one action: the whole loop is padding but the first record
+    ([19, 260], [2]),
+    ([23, 300], [3]),      # cells much narrower than an action step: every pair skips several cells (general walk)
+    ([17, 131], [37]),     # odd number of pairs, lanes past the end of the row in the last block
+    ([9, 40], [201]),      # a tenth of a cell per action: the next-cell fast path of the loop nest, 100 pairs per node
+    ([5, 3], [7]),         # three levels: two cells
+    ([5, 2], [5]),         # two levels: one cell, never a next cell
+])
+def test_emulated_pendulum_loop_nest_edge_shapes(shape, lanes):
+    """The loop nest of sweep_pendulum_kernel (MONO = 2) where its special cases live: padding, cell skips, parked lanes
+    (velocity bounds tight enough that many actions leave the box), damping (the t[a] table holds B.u - g only)."""
+    xd, ud = shape
+    for extra in (dict(), dict(sys_params={"d1": 0.3}, x_lb=[-2.0, -1.5], x_ub=[1.0, 2.5]), dict(alpha=0.9, x_lb=[-3.0, -0.4], x_ub=[3.0, 0.4])):
+        case = dict(system="SinglePendulum", x_grid_dim=xd, u_grid_dim=ud, xbar=[-3.14, 0.0], INF=300.0, **extra)
+        if ud[0] < 4 * lanes and lanes > 1:
+            continue   # the library only splits a node over G lanes when A >= 4 (16 for G = 16)
+        _, grid, cf = build_case(case)
+        P = problem.extract(grid, cf, case.get("alpha", 1.0))
+        J0 = np.random.default_rng(xd[1] + ud[0]).uniform(0, 300, P.N)
+        Jr, pr = c_oracle.sweep_fused(P, J0)
+        for loop in (False, 2):
+            J, pi, _ = emu.sweep(P, J0, lanes=lanes, force_generic=loop)
+            assert np.array_equal(J, Jr) and np.array_equal(pi, pr), (case, loop)
+
+
 @pytest.mark.parametrize("order", ["descending", "shuffled"])
 def test_emulated_pendulum_with_permuted_action_tables(order):
     """Not ascending B.u: the library (and the emulator's copy of its selection rule) must take the generic loop."""
