@@ -189,6 +189,19 @@ int pdp_get_input_from_policy(pdp_handle* h, int32_t k, double* uk_host);
 /* clean_infeasible_set (dynamicprogramming.py:322-334) on the device */
 int pdp_clean_infeasible_set(pdp_handle* h, double tol, int64_t default_action);
 
+/* ---- step after the sweep: batches of closed-loop Euler rollouts under the handle's current policy — what the
+ * reference's examples run to validate a policy (`cl_sys = ctl + sys; cl_sys.compute_trajectory(tf, n, 'euler')`:
+ * simulation.py:298-324 with ClosedLoopSystem.f controller.py:326-355 and LookUpTableController.c
+ * dynamicprogramming.py:85-107), for B initial states at once, one device thread per trajectory:
+ *     u[i] = RGI_linear(u_k tables of pi, fill 0 outside the grid)(x[i]);  x[i+1] = f(x[i], u[i]) * dt + x[i]
+ * Fused systems only (the plant's f is evaluated on the device at arbitrary states: floating-point parity, not bit
+ * parity), whole-grid handles only.  phys[16] = raw physical parameters of the plant:
+ *   PENDULUM {m1, lc1, I1, gravity, d1}   TWOLINK {m1, l1, lc1, I1, m2, lc2, I2, gravity, d1, d2}   CARTPOLE {m1, m2, lcg, gravity}
+ * x0_host (B, n).  Point i is kept when i % stride == 0: n_keep = (npts-1)/stride + 1.  Outputs are laid out
+ * [n_keep][n][B] / [n_keep][m][B] (trajectory index fastest); u_out_host may be NULL. */
+int pdp_rollout(pdp_handle* h, const double* phys, const double* x0_host, int64_t B, int32_t npts, double dt, int32_t stride,
+                double* x_out_host, double* u_out_host);
+
 /* ---- multi-GPU plumbing (one process per GPU; the host layer does the exchange) -------------
  * One asynchronous sweep of this handle's slab on its stream, no host sync.  The new J of the slab
  * is written into the "new" buffer; the caller then exchanges the halo planes of that buffer with

@@ -79,7 +79,46 @@ def main_policy():
               f"INF nodes={int((pe.G == cf.INF).sum())} -> {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+ROLLOUT_CASES = {   # golden case -> (sweeps of the policy used, tf, npts, initial states)
+    "pend_51x51x11": (200, 2.0, 401, [[-3.14, 0.0], [-2.0, 1.0], [0.5, -0.5], [3.0, 2.0], [-6.2, 0.3], [1.0, 6.0]]),
+    "cartpole_swingup": (20, 0.5, 101, [[0.0, 0.1, 0.0, 0.0], [1.0, 3.0, -1.0, 0.5], [-2.0, -3.0, 2.0, -2.0], [5.0, 1.0, 4.0, 4.0]]),
+    "twolink_soft": (30, 0.5, 101, [[0.1, 0.2, 0.0, 0.0], [1.0, -1.0, 0.5, -0.5], [-2.0, 2.5, -1.5, 2.0]]),
+    "dpend_example": (6, 0.5, 101, [[-3.14, 0.0, 0.0, 0.0], [0.5, 0.5, 1.0, -1.0], [-1.0, 1.5, -2.0, 2.0]]),
+}
+
+
+def main_rollouts():
+    """Fixtures of the reference's closed-loop 'euler' simulation under its LookUpTableController
+    (simulation.py:298-324 via ClosedLoopSystem.compute_trajectory controller.py:517-530; dynamicprogramming.py:27-107):
+    policy = pi of the committed value-iteration fixture after the given number of sweeps."""
+    ns = ref_loader.load()
+    for name, (k, tf, npts, x0s) in ROLLOUT_CASES.items():
+        case = CASES[name]
+        gold = np.load(os.path.join(OUT, name + ".npz"))
+        with ref_loader.quiet():
+            sys_, grid, cf, dp = build_reference(ns, case)
+            dp.compute_steps(k)
+            if f"pi_{k}" in gold:
+                assert np.array_equal(dp.pi, gold[f"pi_{k}"])
+            ctl = dp.get_lookup_table_controller()
+            cl_sys = ctl + sys_
+            xs, us = [], []
+            for x0 in x0s:
+                cl_sys.x0 = np.array(x0, dtype=float)
+                traj = cl_sys.compute_trajectory(tf, npts, 'euler')
+                xs.append(traj.x.copy())
+                us.append(traj.u.copy())
+        path = os.path.join(OUT, "rollout_" + name + ".npz")
+        np.savez_compressed(path, sweeps=k, tf=tf, npts=npts, x0=np.array(x0s, float), pi=dp.pi.astype(np.int64),
+                            x=np.array(xs), u=np.array(us))
+        print(f"rollout_{name}: {len(x0s)} trajectories x {npts} points -> {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 if __name__ == "__main__":
+    if "--rollouts-only" in sys.argv:
+        main_rollouts()
+        sys.exit(0)
     if "--policy-only" not in sys.argv:
         main()
     main_policy()
+    main_rollouts()

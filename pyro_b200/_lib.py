@@ -67,6 +67,7 @@ SIGNATURES = {
     "pdp_set_lut": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pdp_build_tables": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pdp_get_input_from_policy": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "pdp_rollout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_int32, C.c_void_p, C.c_void_p]),
     "pdp_clean_infeasible_set": (C.c_int, [C.c_void_p, C.c_double, C.c_int64]),
     "pdp_sweep_async": (C.c_int, [C.c_void_p]),
     "pdp_sweep_planes_async": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),

@@ -30,6 +30,7 @@
 #include "mech2_plan.h"
 
 #include "table_kernels.cuh"
+#include "rollout.cuh"
 
 // exposed for tests: exact_div against IEEE division on the device
 __global__ void exact_div_test_kernel(const double* a, const double* den, double* q_fast, double* q_ieee, long long n) {
@@ -1384,6 +1385,39 @@ extern "C" int pdp_clean_infeasible_set(pdp_handle* h, double tol, int64_t defau
         h->Jv(h->cur_idx) + h->P.slab_node_begin, h->dpi, h->P.INF - tol, h->P.INF, (long long)default_action, n);
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return PDP_OK;
+}
+
+// Batches of closed-loop Euler rollouts under the handle's current policy (rollout.cuh)
+extern "C" int pdp_rollout(pdp_handle* h, const double* phys, const double* x0_host, int64_t B, int32_t npts, double dt,
+                           int32_t stride, double* x_out_host, double* u_out_host) {
+    CHECK_HANDLE(h);
+    const DevProblem& P = h->P;
+    if (P.system_id == PDP_SYS_LUT) return fail(h, PDP_ENOTSUP, "pdp_rollout: needs a fused system (the plant's f is evaluated on the device)");
+    if (h->slab_begin != 0 || h->slab_end != P.dims[0]) return fail(h, PDP_ENOTSUP, "pdp_rollout: the handle must hold the whole grid's policy");
+    if (!phys || !x0_host || !x_out_host) return fail(h, PDP_EINVAL, "pdp_rollout: null pointer");
+    if (B <= 0 || npts < 1 || stride < 1 || !(dt > 0.0)) return fail(h, PDP_EINVAL, "pdp_rollout: B, npts, stride, dt must be positive");
+    const int n = P.n, m = P.m;
+    const long long keep = (npts - 1) / stride + 1;
+    double *dphys = nullptr, *dx0 = nullptr, *dx = nullptr, *du = nullptr;
+    cudaError_t e = cudaMalloc(&dphys, PDP_ROLLOUT_PHYS * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&dx0, (size_t)B * n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&dx, (size_t)keep * n * B * sizeof(double));
+    if (e == cudaSuccess && u_out_host) e = cudaMalloc(&du, (size_t)keep * m * B * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dphys, phys, PDP_ROLLOUT_PHYS * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dx0, x0_host, (size_t)B * n * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        const unsigned blocks = (unsigned)((B + 127) / 128);
+        if (n == 2) rollout_kernel<2><<<blocks, 128, 0, h->stream>>>(P, h->dpi, dphys, dx0, B, npts, dt, stride, dx, du);
+        else rollout_kernel<4><<<blocks, 128, 0, h->stream>>>(P, h->dpi, dphys, dx0, B, npts, dt, stride, dx, du);
+        h->launches += 1;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(x_out_host, dx, (size_t)keep * n * B * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && du) e = cudaMemcpyAsync(u_out_host, du, (size_t)keep * m * B * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(dphys); cudaFree(dx0); cudaFree(dx); cudaFree(du);
+    if (e != cudaSuccess) return fail(h, PDP_ECUDA, std::string("pdp_rollout: ") + cudaGetErrorString(e));
     return PDP_OK;
 }
 

@@ -335,6 +335,19 @@ class DynamicProgramming:
         ctl = make_reference_controller(self.grid_sys, self.pi, u_tables) if hasattr(self.grid_sys, "x_grid_dim") else None
         return ctl if ctl is not None else LookUpTableController(self.grid_sys, self.pi, u_tables)
 
+    def compute_closed_loop_trajectories(self, x0, tf=10, n=10001, stride=1):
+        """Closed-loop Euler trajectories of the plant under the current policy, for a BATCH of initial states on the
+        device: what ``cl_sys = dp.get_lookup_table_controller() + sys; cl_sys.x0 = x0; cl_sys.compute_trajectory(tf, n,
+        'euler')`` computes for one (simulation.py:298-324, controller.py:326-355, dynamicprogramming.py:85-107).
+        x0 (B, n_states) -> t (n_keep,), x (B, n_keep, n_states), u (B, n_keep, m); every ``stride``-th point is kept."""
+        eng = self._engine
+        if eng is None or not hasattr(eng, "rollout"):
+            raise NotImplementedError("closed-loop rollouts need the policy on one device handle (not a sharded / multi-part run)")
+        phys = _problem.plant_parameters(self.sys, eng.problem.system_id)
+        dt = (tf + 0.0 - 0) / (n - 1)
+        x, u = eng.rollout(phys, x0, n, dt, stride)
+        return np.linspace(0, tf, n)[::stride], x, u
+
     def save_latest(self, name='test_data'):
         np.save(name + '_J_inf', self.J_next)
         np.save(name + '_pi_inf', self.pi.astype(int))

@@ -200,6 +200,20 @@ class Engine:
     def clean_infeasible_set(self, tol, default_action):
         self._ck(self.lib.pdp_clean_infeasible_set(self.h, float(tol), int(default_action)))
 
+    def rollout(self, phys, x0, npts, dt, stride=1, with_inputs=True):
+        """B closed-loop Euler trajectories under the current policy (pdp_rollout): x (B, n_keep, n), u (B, n_keep, m)."""
+        x0 = np.ascontiguousarray(np.atleast_2d(np.asarray(x0, dtype=np.float64)))
+        phys = np.ascontiguousarray(phys, dtype=np.float64)
+        n, m = int(self.problem.n), int(self.problem.m)
+        if x0.shape[1] != n or phys.size != 16:
+            raise ValueError("rollout: x0 must be (B, n) and phys 16 doubles")
+        B, keep = x0.shape[0], (int(npts) - 1) // int(stride) + 1
+        x = np.empty((keep, n, B))
+        u = np.empty((keep, m, B)) if with_inputs else None
+        self._ck(self.lib.pdp_rollout(self.h, phys.ctypes.data, x0.ctypes.data, B, int(npts), float(dt), int(stride),
+                                      x.ctypes.data, u.ctypes.data if with_inputs else None))
+        return x.transpose(2, 0, 1), (u.transpose(2, 0, 1) if with_inputs else None)
+
     @property
     def nodes_padded(self):
         return int(self.lib.pdp_nodes_padded(self.h))

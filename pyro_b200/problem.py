@@ -177,6 +177,22 @@ def system_tables(sys, sys_id, x_level):
     return [_f64(t) for t in tabs], par
 
 
+def plant_parameters(sys, sys_id):
+    """Raw physical parameters of a fused plant in the layout pdp_rollout reads (include/pyrodp.h): what the device needs
+    to evaluate f(x, u) at states that are not grid levels (closed-loop rollouts)."""
+    ph = np.zeros(16)
+    if sys_id == _lib.PDP_SYS_PENDULUM:
+        ph[:5] = [sys.m1, sys.lc1, sys.I1, sys.gravity, sys.d1]
+    elif sys_id == _lib.PDP_SYS_TWOLINK:
+        ph[:10] = [sys.m1, sys.l1, sys.lc1, sys.I1, sys.m2, sys.lc2, sys.I2, sys.gravity, sys.d1, sys.d2]
+    elif sys_id == _lib.PDP_SYS_CARTPOLE:
+        ph[:4] = [sys.m1, sys.m2, sys.lcg, sys.gravity]
+    else:
+        raise NotImplementedError("closed-loop rollouts on the device need a fused plant (SinglePendulum, DoublePendulum, "
+                                  "TwoLinkManipulator, CartPole); simulate other systems with the reference's simulator")
+    return ph
+
+
 def extract(grid_sys, cf, alpha=1.0, interpol_method="linear", slab=None, alloc_planes=0, force_lut=False,
             lut_actions=None):
     """Build the descriptor for ``pdp_create``.  ``slab`` = (begin, end) axis-0 planes of this rank.

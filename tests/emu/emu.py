@@ -28,6 +28,8 @@ def load():
         _lib.emu_lut_sweep.argtypes = [C.c_void_p] * 7 + [C.c_int]
         _lib.emu_mech2_evals.restype = C.c_longlong
         _lib.emu_mech2_evals.argtypes = [C.c_int]
+        _lib.emu_rollout.restype = C.c_int
+        _lib.emu_rollout.argtypes = [C.c_void_p] * 4 + [C.c_longlong, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
         _lib.emu_terminal.restype = C.c_int
         _lib.emu_terminal.argtypes = [C.c_void_p] * 3
     return _lib
@@ -95,3 +97,18 @@ def sweep_planes(problem, J_next, J, pi, p0, p1, lanes=1, force_generic=False, m
 def mech2_evals(reset=True):
     """(node, action) pairs the range kernel actually evaluated since the last reset (test instrumentation)."""
     return int(load().emu_mech2_evals(int(reset)))
+
+
+def rollout(problem, pi, phys, x0, npts, dt, stride=1):
+    """The rollout kernel (pdp_rollout) on the CPU: x (B, n_keep, n), u (B, n_keep, m)."""
+    x0 = np.ascontiguousarray(np.atleast_2d(x0), dtype=np.float64)
+    pi = np.ascontiguousarray(pi, dtype=np.int64)
+    phys = np.ascontiguousarray(phys, dtype=np.float64)
+    B, keep = x0.shape[0], (npts - 1) // stride + 1
+    x = np.empty((keep, problem.n, B))
+    u = np.empty((keep, problem.m, B))
+    rc = load().emu_rollout(C.addressof(problem.c), pi.ctypes.data, phys.ctypes.data, x0.ctypes.data, B, int(npts), float(dt),
+                            int(stride), x.ctypes.data, u.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"emu_rollout failed ({rc})")
+    return x.transpose(2, 0, 1), u.transpose(2, 0, 1)

@@ -131,6 +131,7 @@ long long mech2_evals_done = 0;
 extern "C" long long emu_mech2_evals(int reset) { long long v = mech2_evals_done; if (reset) mech2_evals_done = 0; return v; }
 #include "gen/sweep_mech2.cuh"
 #include "gen/mech2_plan.h"
+#include "gen/rollout.cuh"
 
 typedef void (*fused_kernel_t)(const DevProblem, const double*, double*, long long*, unsigned long long*, unsigned int*, double*);
 
@@ -205,6 +206,12 @@ static void fill(const pdp_problem* p, HostProblem& H) {
     }
     P.bu = H.hold(bu.data(), bu.size());
     P.gu = H.hold(p->gu, (size_t)A);
+    std::vector<double> u_flat((size_t)A * p->m);   // input_from_action_id, as pdp_create builds it
+    for (long long a = 0; a < A; ++a) {
+        if (p->m == 1) u_flat[a] = p->u_level[0][a];
+        else { u_flat[2 * a] = p->u_level[0][a / p->udims[1]]; u_flat[2 * a + 1] = p->u_level[1][a % p->udims[1]]; }
+    }
+    P.u_flat = H.hold(u_flat.data(), u_flat.size());
 }
 
 // One backup of axis-0 planes [p0, p1) — the launch pyrodp.cu's launch_planes() makes for a rank's slab (or for a
@@ -315,6 +322,25 @@ extern "C" int emu_terminal(const pdp_problem* p, double* J, long long* pi) {
         emu_launch(grid, block, [&]() {
             if (P.n == 2) terminal_cost_kernel<2>(P, J, pi, 0, P.N);
             else terminal_cost_kernel<4>(P, J, pi, 0, P.N);
+        });
+        return 0;
+    } catch (const std::exception&) {
+        return -3;
+    }
+}
+
+// pdp_rollout's kernel (closed-loop Euler trajectories under a policy), outputs in the device layout [n_keep][n|m][B]
+extern "C" int emu_rollout(const pdp_problem* p, const long long* pi, const double* phys, const double* x0, long long B,
+                           int npts, double dt, int stride, double* x_out, double* u_out) {
+    if (!p || p->system_id == PDP_SYS_LUT) return -1;
+    try {
+        HostProblem H;
+        fill(p, H);
+        DevProblem& P = H.P;
+        emu_uint3 grid = {(unsigned)((B + 127) / 128), 1, 1}, block = {128, 1, 1};
+        emu_launch(grid, block, [&]() {
+            if (P.n == 2) rollout_kernel<2>(P, pi, phys, x0, B, npts, dt, stride, x_out, u_out);
+            else rollout_kernel<4>(P, pi, phys, x0, B, npts, dt, stride, x_out, u_out);
         });
         return 0;
     } catch (const std::exception&) {

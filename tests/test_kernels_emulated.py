@@ -275,3 +275,35 @@ def test_emulated_range_kernel_block_tiles(monkeypatch, tile_rows):
         Jr, pr = c_oracle.sweep_fused(P, J0)
         J, pi, st = emu.sweep(P, J0, lanes=1, mech2="range")
         assert np.array_equal(J, Jr) and np.array_equal(pi, pr) and st[0] == Jr.max()
+
+
+ROLLOUT_FIXTURES = ["pend_51x51x11", "cartpole_swingup", "twolink_soft", "dpend_example"]
+
+
+def rollout_inputs(name):
+    """(Problem, plant parameters, fixture) of a closed-loop rollout fixture (oracle/gen_golden.py: main_rollouts)."""
+    case, gold = CASES[name], load_golden("rollout_" + name)
+    sys_, grid, cf = build_case(case)
+    P = problem.extract(grid, cf, case.get("alpha", 1.0))
+    return P, problem.plant_parameters(sys_, P.system_id), gold
+
+
+def check_rollout(x, u, gold, rtol=1e-9):
+    """Floating-point parity (sin / cos / the 2x2 inverse are evaluated by another library than NumPy's): <= 1e-9 of the
+    trajectory's scale at every kept point, for the states and the interpolated inputs."""
+    scale = max(1.0, np.abs(gold["x"]).max())
+    assert x.shape == gold["x"].shape and u.shape == gold["u"].shape
+    assert np.abs(x - gold["x"]).max() <= rtol * scale, np.abs(x - gold["x"]).max()
+    assert np.abs(u - gold["u"]).max() <= rtol * max(1.0, np.abs(gold["u"]).max()), np.abs(u - gold["u"]).max()
+
+
+@pytest.mark.parametrize("name", ROLLOUT_FIXTURES)
+def test_emulated_rollout_kernel_matches_reference_closed_loop_trajectories(name):
+    """rollout_kernel vs the unmodified reference's `(ctl + sys).compute_trajectory(tf, n, 'euler')`: trajectories that
+    leave the grid (controller output 0 there), 2-D value-first and 4-D weight-first policy interpolation."""
+    P, phys, gold = rollout_inputs(name)
+    npts, tf = int(gold["npts"]), float(gold["tf"])
+    x, u = emu.rollout(P, gold["pi"], phys, gold["x0"], npts, tf / (npts - 1))
+    check_rollout(x, u, gold)
+    xs, us = emu.rollout(P, gold["pi"], phys, gold["x0"], npts, tf / (npts - 1), stride=7)
+    assert np.array_equal(xs, x[:, ::7]) and np.array_equal(us, u[:, ::7])
