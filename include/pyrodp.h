@@ -46,6 +46,10 @@ extern "C" {
 #define PDP_SYS_CARTPOLE 3 /* cart + pole, n=4,m=1              (pyro/dynamic/cartpole.py:322 CartPole)              */
 
 /* cost_id: which stage cost g(x,u) / terminal cost h(x) */
+/* interpolant of J_next in table mode (pdp_set_interpolant) */
+#define PDP_INTERP_LINEAR 0  /* RegularGridInterpolator 'linear' (discretizer.py:570-587): every mode's default          */
+#define PDP_INTERP_SPLINE3 1 /* RectBivariateSpline kx=ky=3, s=0 (discretizer.py:591-612): n = 2, table mode only        */
+
 #define PDP_COST_QUADRATIC 1 /* pyro/analysis/costfunction.py:100-204 QuadraticCostFunction */
 #define PDP_COST_TIME 2      /* pyro/analysis/costfunction.py:287-334 TimeCostFunction      */
 #define PDP_COST_REACH 3     /* pyro/analysis/costfunction.py:421-481 Reachability with the system's own box isavalidstate and the
@@ -176,6 +180,13 @@ int pdp_sweep_host_local(pdp_handle* h, const double* J_held_host, double* J_hos
  * dynamicprogramming.py:523 (INF already folded in).  Uploaded once, then pdp_sweep() runs
  * dynamicprogramming.py:564-570 on the device. */
 int pdp_set_lut(pdp_handle* h, const double* x_next_host, const double* G_host);
+
+/* DynamicProgramming2DRectBivariateSpline (dynamicprogramming.py:578-614): the table sweep with J_next interpolated by the
+ * interpolating bicubic spline scipy's RectBivariateSpline(x_level[0], x_level[1], J_grid, kx=3, ky=3) builds (FITPACK
+ * regrid, not-a-knot knots; arguments outside the grid are clamped to its edge) instead of the RegularGridInterpolator.
+ * Table-mode handles (PDP_SYS_LUT) of 2-D grids holding the whole grid; every pdp_sweep then refits the spline to J_next on
+ * the device (two banded-substitution kernels) before the backup.  Floating-point parity with the reference (<= 1e-9). */
+int pdp_set_interpolant(pdp_handle* h, int32_t which);
 
 /* ---- step before the sweep, for callers that want the reference's dense tables (discretizer.py:342-376
  * compute_xnext_table, dynamicprogramming.py:517-553 compute_cost_lookuptable) of a fused system without the O(N*A)

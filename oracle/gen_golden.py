@@ -114,11 +114,46 @@ def main_rollouts():
         print(f"rollout_{name}: {len(x0s)} trajectories x {npts} points -> {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+SPLINE_CASES = {   # golden case (2-D) -> sweep counts of the snapshots
+    "pend_51x51x11": [1, 5, 20],
+    "pend_time_41x61x7": [1, 4, 12],
+}
+
+
+def main_spline():
+    """Fixtures of the reference's DynamicProgramming2DRectBivariateSpline (dynamicprogramming.py:578-614) on the 2-D
+    value-iteration cases: J / pi snapshots, plus for the last one the reference's Q gap between its best and second
+    best action per node (where it is ~0 the argmin is decided by rounding and a floating-point-parity path may differ)."""
+    ns = ref_loader.load()
+    for name, snaps in SPLINE_CASES.items():
+        case = CASES[name]
+        with ref_loader.quiet():
+            sys_, grid, cf, dp0 = build_reference(ns, case)
+            dp = ns.dynamicprogramming.DynamicProgramming2DRectBivariateSpline(grid, cf)
+            dp.alpha = case.get("alpha", 1.0)
+            out = {"J0": dp.J.copy()}
+            k = 0
+            for target in snaps:
+                dp.compute_steps(target - k)
+                k = target
+                out[f"J_{k}"] = dp.J.copy()
+                out[f"pi_{k}"] = dp.pi.astype(np.int64)
+                Qs = np.sort(dp.Q, axis=1)
+                out[f"gap_{k}"] = Qs[:, 1] - Qs[:, 0]
+        path = os.path.join(OUT, "spline_" + name + ".npz")
+        np.savez_compressed(path, snapshots=np.array(snaps), **out)
+        print(f"spline_{name}: snapshots={snaps} J_max={dp.J.max():.6f} J_min={dp.J.min():.6f} -> {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 if __name__ == "__main__":
     if "--rollouts-only" in sys.argv:
         main_rollouts()
+        sys.exit(0)
+    if "--spline-only" in sys.argv:
+        main_spline()
         sys.exit(0)
     if "--policy-only" not in sys.argv:
         main()
     main_policy()
     main_rollouts()
+    main_spline()

@@ -373,3 +373,15 @@ def lut_sweep(x_level, dims, J_next, x_next, G, alpha=1.0, use_scipy=True):
         Jx = rgi_linear(x_level, grid, x_next)
     Q = G + alpha * Jx
     return Q.min(axis=1), Q.argmin(axis=1)
+
+
+def spline_sweep(x_level, dims, J_next, x_next, G, alpha=1.0):
+    """One backup of the reference's DynamicProgramming2DRectBivariateSpline on given tables
+    (dynamicprogramming.py:582-614; interpolant: discretizer.py:591-612 = scipy RectBivariateSpline kx = ky = 3, s = 0 —
+    third-party FITPACK, executed, not restated).  Returns (J, pi, gap between the best and second-best Q per node)."""
+    from scipy.interpolate import RectBivariateSpline
+    interp = RectBivariateSpline(x_level[0], x_level[1], J_next.reshape(dims), bbox=[None, None, None, None], kx=3, ky=3)
+    Jx = interp(x_next[:, :, 0].flatten(), x_next[:, :, 1].flatten(), grid=False).reshape(G.shape)
+    Q = G + alpha * Jx
+    Qs = np.sort(Q, axis=1)
+    return Q.min(axis=1), Q.argmin(axis=1), Qs[:, 1] - Qs[:, 0]

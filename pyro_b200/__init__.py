@@ -7,6 +7,7 @@ Python interface for that path.
 """
 from . import costfunction, discretizer, dynamicprogramming, systems  # noqa: F401
 from .dynamicprogramming import (DynamicProgramming, DynamicProgrammingWithLookUpTable, LookUpTableController,  # noqa: F401
+                                 DynamicProgramming2DRectBivariateSpline,
                                  PolicyEvaluator, PolicyEvaluatorWithLookUpTable)
 from .discretizer import GridDynamicSystem  # noqa: F401
 

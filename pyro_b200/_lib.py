@@ -12,6 +12,7 @@ PDP_MAX_N, PDP_MAX_M = 4, 2
 PDP_OK, PDP_EINVAL, PDP_ENOTSUP, PDP_ECUDA, PDP_ESTATE = 0, -1, -2, -3, -4
 PDP_SYS_LUT, PDP_SYS_PENDULUM, PDP_SYS_TWOLINK, PDP_SYS_CARTPOLE = 0, 1, 2, 3
 PDP_COST_QUADRATIC, PDP_COST_TIME, PDP_COST_REACH = 1, 2, 3
+PDP_INTERP_LINEAR, PDP_INTERP_SPLINE3 = 0, 1
 
 _dp = C.POINTER(C.c_double)
 
@@ -67,6 +68,7 @@ SIGNATURES = {
     "pdp_set_lut": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pdp_build_tables": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pdp_get_input_from_policy": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "pdp_set_interpolant": (C.c_int, [C.c_void_p, C.c_int32]),
     "pdp_rollout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_int32, C.c_void_p, C.c_void_p]),
     "pdp_clean_infeasible_set": (C.c_int, [C.c_void_p, C.c_double, C.c_int64]),
     "pdp_sweep_async": (C.c_int, [C.c_void_p]),

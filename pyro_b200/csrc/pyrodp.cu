@@ -31,6 +31,7 @@
 
 #include "table_kernels.cuh"
 #include "rollout.cuh"
+#include "spline.cuh"
 
 // exposed for tests: exact_div against IEEE division on the device
 __global__ void exact_div_test_kernel(const double* a, const double* den, double* q_fast, double* q_ieee, long long n) {
@@ -146,6 +147,8 @@ struct pdp_handle {
     int force_lanes = 0;          // test hook (PYRODP_LANES): pin G to 1, 4 or 16
     int policy_blocks = 0;        // one resident wave of sweep_policy_kernel blocks
     bool pend_mono = false;       // pendulum: x_next[1] is non-decreasing along the action list (see sweep_fused.cuh, MONO)
+    bool spline = false;          // LUT mode, n = 2: bicubic-spline interpolant of J_next (pdp_set_interpolant, spline.cuh)
+    SplineDev S{};
     bool force_generic = false;   // test hook (PYRODP_GENERIC=1): use the order-agnostic action loop anyway
     int pend_loop = 2;            // MONO variant of the pendulum kernel: 2 = loop nest (shipped), 1 = round 1's pair loop (PYRODP_PEND_LOOP=1, A/B)
     int mech2_mode = 0;           // 4-D fused systems: 0 order-agnostic kernel, 1 range-skipping kernel
@@ -706,7 +709,7 @@ extern "C" int pdp_kernel_info(const pdp_handle* h, char* out, int32_t len) {
     if (!h || !out || len < 1) return fail(nullptr, PDP_EINVAL, "pdp_kernel_info: bad argument");
     std::string name;
     const DevProblem& P = h->P;
-    if (P.system_id == PDP_SYS_LUT) name = P.A == 1 ? "sweep_policy_kernel" : "sweep_lut_kernel";
+    if (P.system_id == PDP_SYS_LUT) name = P.A == 1 ? "sweep_policy_kernel" : (h->spline ? "sweep_lut_spline_kernel" : "sweep_lut_kernel");
     else if (P.system_id == PDP_SYS_PENDULUM) name = std::string("sweep_pendulum_kernel<") + (h->pend_mono && !h->force_generic ? (h->pend_loop == 2 ? "mono, loop nest" : "mono, pair loop") : "generic") + ">";
     else {
         const char* sys = P.system_id == PDP_SYS_TWOLINK ? "TWOLINK" : "CARTPOLE";
@@ -730,6 +733,36 @@ extern "C" int pdp_set_lut(pdp_handle* h, const double* x_next_host, const doubl
     CUDA_TRY(h, cudaMemcpyAsync(h->d_G, G_host, ng * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->have_lut = true;
+    return PDP_OK;
+}
+
+// DynamicProgramming2DRectBivariateSpline (dynamicprogramming.py:578-614): which interpolant of J_next the table sweep uses
+extern "C" int pdp_set_interpolant(pdp_handle* h, int32_t which) {
+    CHECK_HANDLE(h);
+    if (which == PDP_INTERP_LINEAR) { h->spline = false; return PDP_OK; }
+    if (which != PDP_INTERP_SPLINE3) return fail(h, PDP_EINVAL, "pdp_set_interpolant: unknown interpolant");
+    const DevProblem& P = h->P;
+    if (P.system_id != PDP_SYS_LUT || P.n != 2 || P.A < 2)
+        return fail(h, PDP_ENOTSUP, "pdp_set_interpolant: the bicubic spline needs a table-mode handle of a 2-D grid (discretizer.py:600-612)");
+    if (h->slab_begin != 0 || h->slab_end != P.dims[0]) return fail(h, PDP_ENOTSUP, "pdp_set_interpolant: the spline is fitted on the whole grid; one handle");
+    if (!h->S.coef) {
+        for (int d = 0; d < 2; ++d) {
+            const int m = P.dims[d];
+            std::vector<double> lev((size_t)m), knots, lu;
+            CUDA_TRY(h, cudaMemcpy(lev.data(), P.level[d], (size_t)m * sizeof(double), cudaMemcpyDeviceToHost));
+            if (!spline_plan_axis(lev.data(), m, knots, lu))
+                return fail(h, PDP_ENOTSUP, "pdp_set_interpolant: a cubic spline needs at least 4 levels per axis");
+            int rc;
+            if ((rc = upload(h, knots.data(), knots.size(), &h->S.knots[d])) != PDP_OK) return rc;
+            if ((rc = upload(h, lu.data(), lu.size(), &h->S.lu[d])) != PDP_OK) return rc;
+            h->S.m[d] = m;
+        }
+        void* c = nullptr;
+        CUDA_TRY(h, cudaMalloc(&c, (size_t)P.dims[0] * P.dims[1] * sizeof(double)));
+        h->owned.push_back(c);
+        h->S.coef = (double*)c;
+    }
+    h->spline = true;
     return PDP_OK;
 }
 
@@ -790,6 +823,21 @@ static int launch_planes(pdp_handle* h, int p0, int p1, int stat_set, double* st
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
         // about one resident wave (12 blocks of 128 threads per SM at 40-56 registers) strides over the nodes
         const long long blocks = std::min<long long>((nodes * G + SWEEP_THREADS - 1) / SWEEP_THREADS, (long long)sm_count * 12);
+        if (h->spline) {
+            // DynamicProgramming2DRectBivariateSpline: fit the interpolating bicubic spline of J_next (two sweeps of banded
+            // substitutions), then the table sweep with the spline evaluation
+            spline_fit_axis0_kernel<<<(unsigned)((P.dims[1] + 127) / 128), 128, 0, stream>>>(Jn, h->S);
+            spline_fit_axis1_kernel<<<(unsigned)((P.dims[0] + 127) / 128), 128, 0, stream>>>(h->S);
+            h->launches += 2;
+            switch (G) {
+#define SPL_CASE(g) case g: sweep_lut_spline_kernel<g><<<(unsigned)blocks, SWEEP_THREADS, 0, stream>>>(P, h->S, Jn, Jo, h->piv(), h->d_xnext, h->d_G, slots, counter, stats); break;
+                SPL_CASE(1) SPL_CASE(2) SPL_CASE(4) SPL_CASE(8) SPL_CASE(16) SPL_CASE(32)
+#undef SPL_CASE
+            }
+            CUDA_TRY(h, cudaGetLastError());
+            h->launches += 1;
+            return PDP_OK;
+        }
         if (P.n == 2) launch_lut<2>(h, stream, P, G, (unsigned)blocks, Jn, Jo, slots, counter, stats);
         else if (P.n == 3) launch_lut<3>(h, stream, P, G, (unsigned)blocks, Jn, Jo, slots, counter, stats);
         else launch_lut<4>(h, stream, P, G, (unsigned)blocks, Jn, Jo, slots, counter, stats);
@@ -1175,6 +1223,7 @@ static int sweep_host_impl(pdp_handle* h, const double* J_next_host, long long h
     if (h->slab_end <= h->slab_begin) return fail(h, PDP_ESTATE, "pdp_sweep_host: this handle computes no planes");
     if (h->enqueued || h->pending) return fail(h, PDP_ESTATE, "pdp_sweep_host: collect / commit the outstanding sweeps first");
     if (h->P.system_id == PDP_SYS_LUT && !h->have_lut) return fail(h, PDP_ESTATE, "pdp_sweep: LUT mode needs pdp_set_lut first");
+    if (h->spline) return fail(h, PDP_ENOTSUP, "pdp_sweep_host: the spline interpolant is fitted on the whole J_next before a sweep; use pdp_set_J + pdp_sweep");
     int C = 8;
     if (const char* env = getenv("PYRODP_HOST_CHUNKS")) C = atoi(env);
     C = std::max(1, std::min(std::min(C, PDP_HOST_MAX_CHUNKS), h->slab_end - h->slab_begin));

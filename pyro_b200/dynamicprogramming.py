@@ -372,6 +372,28 @@ class DynamicProgrammingWithLookUpTable(DynamicProgramming):
     _invalid_input_is_exact_inf = False
 
 
+class DynamicProgramming2DRectBivariateSpline(DynamicProgrammingWithLookUpTable):
+    """dynamicprogramming.py:578-614: the table sweep with J_next interpolated by scipy's RectBivariateSpline(kx=3, ky=3)
+    — the interpolating bicubic spline, arguments outside the grid clamped to its edge — instead of the
+    RegularGridInterpolator.  2-D grids only (discretizer.py:600-612 raises NotImplementedError otherwise).  Always table
+    mode, as in the reference (Q = G + alpha * J_interpol(x_next_table)); the spline is refitted to J_next on the device
+    before every backup (pdp_set_interpolant).  Floating-point parity with the reference, not bit parity."""
+
+    def _extract(self):
+        if self.sys.n != 2:
+            raise NotImplementedError("the bivariate-spline interpolant exists for 2-D grids only (discretizer.py:600-612)")
+        return _problem.extract(self.grid_sys, self.cf, self.alpha, self.interpol_method, force_lut=True)
+
+    def _make_engine(self, P):
+        if self._engine_factory is not None:
+            eng = self._engine_factory(self, P)
+            eng.set_lut(*build_lookup_tables(self.grid_sys, self.cf, self.tf, exact_inf=False))
+        else:
+            eng = self._make_lut_engine(P)
+        eng.set_interpolant("spline3")
+        return eng
+
+
 class PolicyEvaluator(DynamicProgramming):
     """Evaluate the cost-to-go of a given control law (dynamicprogramming.py:619-672): the backup
     J[s] = g(x_s, u_s)*dt + alpha*J_next(x_next_s) with u_s = ctl.c(x_s, ctl.rbar, t), INF where the

@@ -200,6 +200,12 @@ class Engine:
     def clean_infeasible_set(self, tol, default_action):
         self._ck(self.lib.pdp_clean_infeasible_set(self.h, float(tol), int(default_action)))
 
+    def set_interpolant(self, which):
+        """'linear' (RegularGridInterpolator, the default) or 'spline3' (RectBivariateSpline kx = ky = 3: table-mode handles
+        of 2-D grids, dynamicprogramming.py:578-614)."""
+        code = {"linear": _lib.PDP_INTERP_LINEAR, "spline3": _lib.PDP_INTERP_SPLINE3}[which]
+        self._ck(self.lib.pdp_set_interpolant(self.h, code))
+
     def rollout(self, phys, x0, npts, dt, stride=1, with_inputs=True):
         """B closed-loop Euler trajectories under the current policy (pdp_rollout): x (B, n_keep, n), u (B, n_keep, m)."""
         x0 = np.ascontiguousarray(np.atleast_2d(np.asarray(x0, dtype=np.float64)))

@@ -28,6 +28,8 @@ def load():
         _lib.emu_lut_sweep.argtypes = [C.c_void_p] * 7 + [C.c_int]
         _lib.emu_mech2_evals.restype = C.c_longlong
         _lib.emu_mech2_evals.argtypes = [C.c_int]
+        _lib.emu_spline_sweep.restype = C.c_int
+        _lib.emu_spline_sweep.argtypes = [C.c_void_p] * 7 + [C.c_int, C.c_void_p]
         _lib.emu_rollout.restype = C.c_int
         _lib.emu_rollout.argtypes = [C.c_void_p] * 4 + [C.c_longlong, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
         _lib.emu_terminal.restype = C.c_int
@@ -112,3 +114,20 @@ def rollout(problem, pi, phys, x0, npts, dt, stride=1):
     if rc != 0:
         raise RuntimeError(f"emu_rollout failed ({rc})")
     return x.transpose(2, 0, 1), u.transpose(2, 0, 1)
+
+
+def spline_sweep(problem, J_next, x_next, G, grid_blocks=24):
+    """One backup of the bicubic-spline table sweep (pdp_set_interpolant(PDP_INTERP_SPLINE3)): the two fit kernels, then
+    sweep_lut_spline_kernel: (J, pi, stats, B-spline coefficients (m0, m1))."""
+    J_next = np.ascontiguousarray(J_next, dtype=np.float64)
+    x_next = np.ascontiguousarray(x_next, dtype=np.float64)
+    G = np.ascontiguousarray(G, dtype=np.float64)
+    J = np.empty(problem.N)
+    pi = np.empty(problem.N, dtype=np.int64)
+    stats = np.empty(3)
+    coef = np.empty(problem.N)
+    rc = load().emu_spline_sweep(C.addressof(problem.c), J_next.ctypes.data, x_next.ctypes.data, G.ctypes.data, J.ctypes.data,
+                                 pi.ctypes.data, stats.ctypes.data, int(grid_blocks), coef.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"emu_spline_sweep failed ({rc})")
+    return J, pi, stats, coef

@@ -132,6 +132,7 @@ extern "C" long long emu_mech2_evals(int reset) { long long v = mech2_evals_done
 #include "gen/sweep_mech2.cuh"
 #include "gen/mech2_plan.h"
 #include "gen/rollout.cuh"
+#include "gen/spline.cuh"
 
 typedef void (*fused_kernel_t)(const DevProblem, const double*, double*, long long*, unsigned long long*, unsigned int*, double*);
 
@@ -341,6 +342,43 @@ extern "C" int emu_rollout(const pdp_problem* p, const long long* pi, const doub
         emu_launch(grid, block, [&]() {
             if (P.n == 2) rollout_kernel<2>(P, pi, phys, x0, B, npts, dt, stride, x_out, u_out);
             else rollout_kernel<4>(P, pi, phys, x0, B, npts, dt, stride, x_out, u_out);
+        });
+        return 0;
+    } catch (const std::exception&) {
+        return -3;
+    }
+}
+
+// pdp_set_interpolant(PDP_INTERP_SPLINE3) + one sweep: the plan, the two fit kernels and the spline table sweep as
+// launch_planes() issues them.  coef_out (optional): the fitted B-spline coefficients.
+extern "C" int emu_spline_sweep(const pdp_problem* p, const double* J_next, const double* x_next, const double* Gtab, double* J,
+                                long long* pi, double* stats3, int grid_blocks, double* coef_out) {
+    if (!p || p->system_id != PDP_SYS_LUT || p->n != 2) return -1;
+    try {
+        HostProblem H;
+        fill(p, H);
+        DevProblem& P = H.P;
+        SplineDev S{};
+        std::vector<double> knots[2], lu[2], coef((size_t)P.dims[0] * P.dims[1]);
+        for (int d = 0; d < 2; ++d) {
+            if (!spline_plan_axis(P.level[d], P.dims[d], knots[d], lu[d])) return -2;
+            S.knots[d] = knots[d].data(); S.lu[d] = lu[d].data(); S.m[d] = P.dims[d];
+        }
+        S.coef = coef.data();
+        emu_uint3 b128 = {128, 1, 1};
+        emu_launch(emu_uint3{(unsigned)((P.dims[1] + 127) / 128), 1, 1}, b128, [&]() { spline_fit_axis0_kernel(J_next, S); });
+        emu_launch(emu_uint3{(unsigned)((P.dims[0] + 127) / 128), 1, 1}, b128, [&]() { spline_fit_axis1_kernel(S); });
+        if (coef_out) memcpy(coef_out, coef.data(), coef.size() * sizeof(double));
+        std::vector<unsigned long long> slots(3 * STATS_SLOTS, 0);
+        unsigned int counter = 0;
+        int G = 1;
+        while (G < 32 && G < P.A) G <<= 1;
+        const long long blocks = std::min<long long>((P.N * G + SWEEP_THREADS - 1) / SWEEP_THREADS, grid_blocks);
+        emu_uint3 grid = {(unsigned)blocks, 1, 1}, block = {SWEEP_THREADS, 1, 1};
+#define EMU_SPL(GG) sweep_lut_spline_kernel<GG>(P, S, J_next, J, pi, x_next, Gtab, slots.data(), &counter, stats3)
+        emu_launch(grid, block, [&]() {
+            switch (G) { case 1: EMU_SPL(1); break; case 2: EMU_SPL(2); break; case 4: EMU_SPL(4); break;
+                         case 8: EMU_SPL(8); break; case 16: EMU_SPL(16); break; default: EMU_SPL(32); }
         });
         return 0;
     } catch (const std::exception&) {

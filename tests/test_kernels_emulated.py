@@ -307,3 +307,113 @@ def test_emulated_rollout_kernel_matches_reference_closed_loop_trajectories(name
     check_rollout(x, u, gold)
     xs, us = emu.rollout(P, gold["pi"], phys, gold["x0"], npts, tf / (npts - 1), stride=7)
     assert np.array_equal(xs, x[:, ::7]) and np.array_equal(us, u[:, ::7])
+
+
+SPLINE_FIXTURES = ["pend_51x51x11", "pend_time_41x61x7"]
+
+
+def check_spline_snapshot(J, pi, gold, k, rtol=1e-9):
+    """Floating-point parity of the spline variant: J within rtol of the reference's scale; pi equal wherever the
+    reference's own best and second-best Q differ by more than that tolerance (elsewhere rounding decides the argmin)."""
+    J_ref, pi_ref, gap = gold[f"J_{k}"], gold[f"pi_{k}"], gold[f"gap_{k}"]
+    scale = np.abs(J_ref).max()
+    assert np.abs(J - J_ref).max() <= rtol * scale, (k, np.abs(J - J_ref).max(), scale)
+    differ = pi != pi_ref
+    assert not (differ & (gap > 10 * rtol * scale)).any(), (k, int(differ.sum()))
+    return int(differ.sum())
+
+
+@pytest.mark.parametrize("name", SPLINE_FIXTURES)
+def test_emulated_spline_sweep_matches_reference_spline_class(name):
+    """pdp_set_interpolant(SPLINE3): host plan (knots, banded LU), the two fit kernels and sweep_lut_spline_kernel against
+    the unmodified reference's DynamicProgramming2DRectBivariateSpline (scipy RectBivariateSpline kx = ky = 3)."""
+    from pyro_b200 import dynamicprogramming
+    case, gold = CASES[name], load_golden("spline_" + name)
+    _, grid, cf = build_case(case, lookup=True)
+    alpha = case.get("alpha", 1.0)
+    P = problem.extract(grid, cf, alpha, force_lut=True)
+    x_next, G = dynamicprogramming.build_lookup_tables(grid, cf, exact_inf=False)
+    J, k = gold["J0"], 0
+    for target in gold["snapshots"][:2]:
+        while k < target:
+            J_prev = J
+            J, pi, st, coef = emu.spline_sweep(P, J_prev, x_next, G)
+            k += 1
+            d = J - J_prev
+            assert st[0] == J.max() and st[1] == d.max() and st[2] == d.min()
+        check_spline_snapshot(J, pi, gold, k)
+
+
+def test_emulated_spline_fit_equals_scipy_coefficients():
+    """The device fit (banded substitutions) against FITPACK's own coefficients on rough data and a non-square grid."""
+    from scipy.interpolate import RectBivariateSpline
+    from pyro_b200 import dynamicprogramming
+    case = dict(system="SinglePendulum", x_grid_dim=[4, 37], u_grid_dim=[3], xbar=[-3.14, 0.0], INF=300.0)
+    _, grid, cf = build_case(case, lookup=True)
+    P = problem.extract(grid, cf, 0.9, force_lut=True)
+    x_next, G = dynamicprogramming.build_lookup_tables(grid, cf, exact_inf=False)
+    J0 = np.random.default_rng(3).uniform(-50, 300, P.N)
+    J, pi, _, coef = emu.spline_sweep(P, J0, x_next, G)
+    sp = RectBivariateSpline(grid.x_level[0], grid.x_level[1], J0.reshape(grid.x_grid_dim), kx=3, ky=3)
+    assert np.abs(coef - sp.get_coeffs()).max() <= 1e-10 * np.abs(sp.get_coeffs()).max()
+    Q = G + 0.9 * sp(x_next[:, :, 0].flatten(), x_next[:, :, 1].flatten(), grid=False).reshape(G.shape)
+    assert np.abs(J - Q.min(axis=1)).max() <= 1e-10 * np.abs(Q.min(axis=1)).max()
+
+
+class EmuSplineEngine:
+    """Engine interface of a table-mode handle in spline mode, backed by the emulated kernels (host-logic test of the
+    DynamicProgramming2DRectBivariateSpline mirror without a GPU)."""
+
+    def __init__(self, P):
+        self.problem, self.N = P, P.N
+        self.J = self.J_next = self.pi = None
+        self.launch_count, self.interpolant = 0, "linear"
+        self.kernel_info = "sweep_lut_spline_kernel (emulated)"
+
+    def set_lut(self, x_next, G):
+        self.x_next, self.G = x_next, G
+
+    def set_interpolant(self, which):
+        self.interpolant = which
+
+    def set_J(self, J):
+        self.J = np.array(J, dtype=float)
+
+    def get_J(self):
+        return self.J.copy()
+
+    def get_J_next(self):
+        return self.J_next.copy()
+
+    def get_pi(self):
+        return self.pi.copy()
+
+    def sweep(self, n=1):
+        assert self.interpolant == "spline3"
+        out = np.empty((n, 3))
+        for k in range(n):
+            self.J_next = self.J
+            self.J, self.pi, out[k], _ = emu.spline_sweep(self.problem, self.J_next, self.x_next, self.G)
+            self.launch_count += 3
+        return out
+
+    def close(self):
+        pass
+
+
+def test_spline_mirror_class_drives_a_table_mode_engine():
+    from pyro_b200 import dynamicprogramming
+    name = "pend_time_41x61x7"
+    case, gold = CASES[name], load_golden("spline_" + name)
+    _, grid, cf = build_case(case, lookup=True)
+    dp = dynamicprogramming.DynamicProgramming2DRectBivariateSpline(grid, cf, engine_factory=lambda dp, P: EmuSplineEngine(P))
+    dp.verbose = False
+    assert dp._engine.problem.system_id == 0 and dp._engine.interpolant == "spline3"      # forced table mode
+    assert np.array_equal(dp.J, gold["J0"])
+    k = int(gold["snapshots"][0])
+    dp.compute_steps(k)
+    check_spline_snapshot(dp.J, dp.pi, gold, k)
+    assert dp.k == k and dp.J_next.shape == dp.J.shape
+    _, grid4, cf4 = build_case(CASES["twolink_9"])
+    with pytest.raises(NotImplementedError):
+        dynamicprogramming.DynamicProgramming2DRectBivariateSpline(grid4, cf4, engine_factory=lambda dp, P: EmuSplineEngine(P))
