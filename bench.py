@@ -540,7 +540,7 @@ def run_workload(ctx, args, wl_key, primary):
         "fp64_issue": fp64, "l1_data_pipe": l1,
         "fp64_inst_per_eval": ncu["fp64_warp_inst"] * 32.0 / evals_per_step if ncu.get("fp64_warp_inst") else None,
         "l1_wavefronts_per_warp_eval": ncu["l1_wavefronts"] * 32.0 / evals_per_step if ncu.get("l1_wavefronts") else None,
-        "ncu_pct": ncu.get("ncu_pct"), "counters_source": ncu.get("source"),
+        "ncu_pct": ncu.get("ncu_pct"), "counters_source": ncu.get("source"), "counters_kernel": ncu.get("kernel"),
         "traffic_over_compulsory": (dram / (24.0 * N)) if dram else None,
         "compulsory_dram_bytes_per_launch": 24.0 * N / world,
         "dram": {"achieved": (dram / world) / kernel_s / 1e9, "peak": peak_hbm, "unit": "GB/s",

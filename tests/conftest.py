@@ -37,6 +37,13 @@ def load_golden(name):
 
 
 def has_gpu():
+    """A usable CUDA device?  Asked of the library itself (cudaGetDeviceCount through pdp_device_count), so that GPU runs do
+    not pay for `import torch`; torch is the fallback when the library is not built yet."""
+    try:
+        from pyro_b200.engine import device_count
+        return device_count() > 0
+    except Exception:
+        pass
     try:
         import torch
         return torch.cuda.is_available()

@@ -196,6 +196,35 @@ def test_pendulum_order_agnostic_loop_on_mid_size_and_descending_inputs(monkeypa
         eng.close()
 
 
+@pytest.mark.parametrize("loop", ["1", "2"])
+def test_pendulum_loop_nest_and_pair_loop_on_edge_shapes(loop, monkeypatch):
+    """Both MONO loops of sweep_pendulum_kernel (PYRODP_PEND_LOOP: 2 = loop nest, shipped; 1 = round 1's pair loop) where
+    their special cases live — padding records, cells narrower than an action step, parked lanes, damping, two-level
+    axes — on rough J against the C oracle, for every lane split the library may choose."""
+    monkeypatch.setenv("PYRODP_PEND_LOOP", loop)
+    shapes = [([19, 260], [1]), ([19, 260], [2]), ([23, 300], [3]), ([17, 131], [37]), ([9, 40], [201]), ([5, 3], [7]), ([5, 2], [5]),
+              ([301, 517], [64])]
+    extras = [dict(), dict(sys_params={"d1": 0.3}, x_lb=[-2.0, -1.5], x_ub=[1.0, 2.5]), dict(alpha=0.9, x_lb=[-3.0, -0.4], x_ub=[3.0, 0.4])]
+    for (xd, ud) in shapes:
+        for extra in extras:
+            case = dict(system="SinglePendulum", x_grid_dim=xd, u_grid_dim=ud, xbar=[-3.14, 0.0], INF=300.0, **extra)
+            _, grid, cf = build_case(case)
+            P = problem.extract(grid, cf, case.get("alpha", 1.0))
+            J0 = np.random.default_rng(xd[1] + ud[0]).uniform(0, 300, P.N)
+            Jr, pr = c_oracle.sweep_fused(P, J0)
+            for lanes in (0, 1, 4, 16):
+                if lanes > 1 and ud[0] < 4 * lanes:
+                    continue
+                monkeypatch.setenv("PYRODP_LANES", str(lanes))
+                eng = Engine(P)
+                want = "loop nest" if loop == "2" else "pair loop"
+                assert want in eng.kernel_info, eng.kernel_info
+                eng.set_J(J0)
+                eng.sweep(1)
+                assert np.array_equal(eng.get_J(), Jr) and np.array_equal(eng.get_pi(), pr), (case, lanes)
+                eng.close()
+
+
 def test_full_size_config2_sampled_against_oracle_and_properties():
     """BASELINE config 2 (SinglePendulum 1001x1001x201) at full size: random node ranges against the C
     oracle, plus size-independent properties (determinism, monotonicity of the Bellman operator,
