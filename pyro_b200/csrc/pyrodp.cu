@@ -150,7 +150,8 @@ struct pdp_handle {
     bool spline = false;          // LUT mode, n = 2: bicubic-spline interpolant of J_next (pdp_set_interpolant, spline.cuh)
     SplineDev S{};
     bool force_generic = false;   // test hook (PYRODP_GENERIC=1): use the order-agnostic action loop anyway
-    int pend_loop = 2;            // MONO variant of the pendulum kernel: 2 = loop nest (shipped), 1 = round 1's pair loop (PYRODP_PEND_LOOP=1, A/B)
+    int pend_loop = 1;            // MONO variant of the pendulum kernel: 1 = pair loop (shipped), 2 = loop nest (PYRODP_PEND_LOOP=2; 11 % fewer
+                                  // non-FP64 instructions, same sweep time: profiles/r02p_pendulum_loops_ab.jsonl)
     int mech2_mode = 0;           // 4-D fused systems: 0 order-agnostic kernel, 1 range-skipping kernel
     int force_mech2 = -1;         // test / A-B hook (PYRODP_MECH2=generic|range)
     int test_interior_delay_us = 0;   // test hook (PYRODP_TEST_INTERIOR_DELAY_US): spin before the interior planes of a sharded sweep
@@ -437,7 +438,7 @@ extern "C" int pdp_create(const pdp_problem* p, pdp_handle** out) {
     if (cudaGetDevice(&h->device) != cudaSuccess) { g_err = "cudaGetDevice failed"; return bail(PDP_ECUDA); }
     if (const char* env = getenv("PYRODP_LANES")) h->force_lanes = atoi(env);
     if (const char* env = getenv("PYRODP_GENERIC")) h->force_generic = atoi(env) != 0;
-    if (const char* env = getenv("PYRODP_PEND_LOOP")) h->pend_loop = (atoi(env) == 1) ? 1 : 2;
+    if (const char* env = getenv("PYRODP_PEND_LOOP")) h->pend_loop = (atoi(env) == 2) ? 2 : 1;
     if (const char* env = getenv("PYRODP_TEST_INTERIOR_DELAY_US")) h->test_interior_delay_us = atoi(env);
     if (const char* env = getenv("PYRODP_MECH2"))
         h->force_mech2 = !strcmp(env, "generic") ? 0 : !strcmp(env, "range") ? 1 : -1;

@@ -125,7 +125,13 @@ __device__ __forceinline__ void stage(double* dst, const double* __restrict__ sr
 // MONO = the host verified that x_next[1] cannot decrease along the action list (B.u ascending,
 // inv(H) > 0, dt > 0, every action allowed — the linspace input grid of a pendulum): then lo <= x
 // holds by induction, one compare (x < hi) on the later action of a pair covers both, the cell only
-// ever moves up, and a lane whose x_next passed the upper bound is finished.
+// ever moves up, and a lane whose x_next passed the upper bound is finished.  MONO = 1: pairs of actions under one vote,
+// the cell change inlined at both actions (round 1, the shipped loop).  MONO = 2 (PYRODP_PEND_LOOP=2): the loop nest
+// further down — 11 % fewer non-FP64 instructions (ncu r02p: 16.5 instead of 18.7 per warp-eval, issue slots 67 -> 63 %)
+// and the SAME sweep time (0.311 ms at cfg 2 for both, one process, profiles/r02p_pendulum_loops_ab.jsonl): the kernel
+// does not sit on the issue port, as round 1's count model (above) had it, but on the FP64 pipe, which the four
+// sub-partitions of an SM share (sm__pipe_shared_cycles_active = sm__pipe_fp64_cycles_active = 68 %; stall reasons:
+// fixed-latency wait 3.2, math-pipe throttle 1.7 warps per issued instruction).  Kept as a measured alternative.
 #ifndef PEND_MIN_BLOCKS
 #define PEND_MIN_BLOCKS 8
 #endif
@@ -273,10 +279,9 @@ sweep_pendulum_kernel(const __grid_constant__ DevProblem P, const double* __rest
     } else if constexpr (MONO == 2) {
         // Loop nest.  The inner loop runs the pairs of actions the cached cell still covers for EVERY lane of the warp
         // (one compare on the later action of a pair and one vote per pair, the cell state loop-invariant, two pairs per
-        // pass): 35 FP64 + 11.5 other instructions per pair.  The outer loop handles the pair at which some lane leaves
-        // its cell.  ncu r01K had counted 18.6 non-FP64 instructions per eval for the MONO = 1 loop, half of them on the
-        // cell changes (one pair in five at cfg 2) and 3 per eval re-deriving the shared-memory address of the action
-        // record; the static count of this loop is 5.75 per eval on the common path.
+        // pass): 35 FP64 + 11.5 other instructions per pair on the common path (static count; MONO = 1: 35 + 18).  The
+        // outer loop handles the pair at which some lane leaves its cell.  Measured (ncu r02p): 19.4 FP64 + 16.5 other
+        // instructions per warp-eval against 19.5 + 18.7 — and no change of the sweep time (note above the kernel).
         double gxv = gx;
         auto evalq = [&](double x, double gu) {
             const double y1 = exact_div(x - lo, den, rinv);

@@ -2,7 +2,7 @@
 of sweep_pendulum_kernel — ms per sweep (CUDA events inside pdp_sweep, J resident, no L2 flush: use for A/B only) and
 bit equality of J / pi between the loops after the timed sweeps.
 
-    python scripts/probe_pend.py                 # loop nest (shipped) and round 1's pair loop, same library
+    python scripts/probe_pend.py                 # loop nest (PYRODP_PEND_LOOP=2) and the shipped pair loop, same library
     PYRODP_LIB=pyro_b200/libpyrodp_b9.so python scripts/probe_pend.py nest     # another build of the library
     python scripts/probe_pend.py nest --sweeps 6 # short run for ncu
 """
@@ -22,8 +22,8 @@ LOOPS = {"nest": "2", "pair": "1"}
 
 
 def main():
-    args = [a for a in sys.argv[1:] if not a.startswith("--")]
     sweeps = int(sys.argv[sys.argv.index("--sweeps") + 1]) if "--sweeps" in sys.argv else 200
+    args = [a for a in sys.argv[1:] if a in LOOPS]
     _, g, cf = build_case(CFG2)
     evals = float(g.nodes_n) * g.actions_n
     results = {}

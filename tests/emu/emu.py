@@ -42,7 +42,7 @@ MECH2_MODES = {None: 0, "generic": 1, "range": 0}
 
 def _mode(force_generic, mech2):
     """Kernel selection code of emu_sweep*: 0 = as the library selects (the 4-D range kernel for one lane per node when the
-    action table allows it), 1 = the order-agnostic kernels, 2 = round 1's pendulum pair loop (PYRODP_PEND_LOOP=1)."""
+    action table allows it), 1 = the order-agnostic kernels, 2 = the pendulum kernel's loop nest (PYRODP_PEND_LOOP=2)."""
     return int(force_generic) if force_generic else MECH2_MODES[mech2]
 
 

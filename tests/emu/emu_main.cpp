@@ -226,8 +226,8 @@ extern "C" int emu_sweep_planes(const pdp_problem* p, const double* J_next, doub
         DevProblem& P = H.P;
         const int G = lanes;
         const bool a1 = P.alpha_is_one != 0, nd = (P.system_id == PDP_SYS_PENDULUM) && P.par[1] == 0.0;
-        // force_generic: 0 = what the library selects, 1 = order-agnostic kernels, 2 = round 1's pendulum pair loop (PYRODP_PEND_LOOP=1)
-        const int mono = (H.mono && force_generic != 1) ? (force_generic == 2 ? 1 : 2) : 0;
+        // force_generic: 0 = what the library selects, 1 = order-agnostic kernels, 2 = the pendulum kernel's loop nest (PYRODP_PEND_LOOP=2)
+        const int mono = (H.mono && force_generic != 1) ? (force_generic == 2 ? 2 : 1) : 0;
         fused_kernel_t k = nullptr;
         if (G == 1) k = a1 ? fused_for<1, true>(P.system_id, nd, mono) : fused_for<1, false>(P.system_id, nd, mono);
         else if (G == 4) k = a1 ? fused_for<4, true>(P.system_id, nd, mono) : fused_for<4, false>(P.system_id, nd, mono);

@@ -52,8 +52,9 @@ def test_emulated_order_agnostic_pendulum_loop(name, lanes):
 
 @pytest.mark.parametrize("lanes", [1, 4, 16])
 @pytest.mark.parametrize("name", ["pend_51x51x11", "pend_time_41x61x7", "pend_reach_41x41x3"])
-def test_emulated_round1_pair_loop_of_the_pendulum_kernel(name, lanes):
-    """PYRODP_PEND_LOOP=1 (kept for A/B): the pair loop the loop nest replaced."""
+def test_emulated_loop_nest_of_the_pendulum_kernel(name, lanes):
+    """PYRODP_PEND_LOOP=2: the loop-nest variant of the MONO action loop (fewer instructions, same sweep time on a B200;
+    the pair loop stays the default and is what every other test runs)."""
     case, gold = CASES[name], load_golden(name)
     _, grid, cf = build_case(case)
     P = problem.extract(grid, cf, case.get("alpha", 1.0))
@@ -73,8 +74,9 @@ def test_emulated_round1_pair_loop_of_the_pendulum_kernel(name, lanes):
     ([5, 2], [5]),         # two levels: one cell, never a next cell
 ])
 def test_emulated_pendulum_loop_nest_edge_shapes(shape, lanes):
-    """The loop nest of sweep_pendulum_kernel (MONO = 2) where its special cases live: padding, cell skips, parked lanes
-    (velocity bounds tight enough that many actions leave the box), damping (the t[a] table holds B.u - g only)."""
+    """Both MONO loops of sweep_pendulum_kernel (pair loop = default, loop nest = PYRODP_PEND_LOOP=2) where their special
+    cases live: padding, cell skips, parked lanes (velocity bounds tight enough that many actions leave the box), damping
+    (the t[a] table holds B.u - g only)."""
     xd, ud = shape
     for extra in (dict(), dict(sys_params={"d1": 0.3}, x_lb=[-2.0, -1.5], x_ub=[1.0, 2.5]), dict(alpha=0.9, x_lb=[-3.0, -0.4], x_ub=[3.0, 0.4])):
         case = dict(system="SinglePendulum", x_grid_dim=xd, u_grid_dim=ud, xbar=[-3.14, 0.0], INF=300.0, **extra)

@@ -198,7 +198,7 @@ def test_pendulum_order_agnostic_loop_on_mid_size_and_descending_inputs(monkeypa
 
 @pytest.mark.parametrize("loop", ["1", "2"])
 def test_pendulum_loop_nest_and_pair_loop_on_edge_shapes(loop, monkeypatch):
-    """Both MONO loops of sweep_pendulum_kernel (PYRODP_PEND_LOOP: 2 = loop nest, shipped; 1 = round 1's pair loop) where
+    """Both MONO loops of sweep_pendulum_kernel (PYRODP_PEND_LOOP: 1 = pair loop, shipped; 2 = loop nest) where
     their special cases live — padding records, cells narrower than an action step, parked lanes, damping, two-level
     axes — on rough J against the C oracle, for every lane split the library may choose."""
     monkeypatch.setenv("PYRODP_PEND_LOOP", loop)
