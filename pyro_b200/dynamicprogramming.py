@@ -384,14 +384,46 @@ class DynamicProgramming2DRectBivariateSpline(DynamicProgrammingWithLookUpTable)
             raise NotImplementedError("the bivariate-spline interpolant exists for 2-D grids only (discretizer.py:600-612)")
         return _problem.extract(self.grid_sys, self.cf, self.alpha, self.interpol_method, force_lut=True)
 
+    def _fused_twin(self):
+        """Descriptor of the same problem on a fused kernel, or None: lets the tables and the terminal cost of a plant the
+        library knows come from the device (pdp_build_tables, pdp_eval_terminal_cost) instead of O(N*A) Python loops."""
+        if self._engine_factory is not None or self.time_varying:
+            return None
+        P = _problem.extract(self.grid_sys, self.cf, self.alpha, self.interpol_method)
+        return None if P.system_id == _lib.PDP_SYS_LUT else P
+
     def _make_engine(self, P):
         if self._engine_factory is not None:
             eng = self._engine_factory(self, P)
             eng.set_lut(*build_lookup_tables(self.grid_sys, self.cf, self.tf, exact_inf=False))
         else:
-            eng = self._make_lut_engine(P)
+            twin = self._fused_twin()
+            if twin is None:
+                eng = self._make_lut_engine(P)
+            else:
+                src = Engine(twin)
+                try:
+                    x_next, _, G = src.build_tables(x_ok=False)      # G = g*dt where input and arrival state are allowed, else INF
+                finally:
+                    src.close()
+                eng = Engine(P)
+                eng.set_lut(x_next, G)
         eng.set_interpolant("spline3")
         return eng
+
+    def evaluate_terminal_cost(self):
+        twin = self._fused_twin()
+        if twin is None:
+            return super().evaluate_terminal_cost()
+        src = Engine(twin)
+        try:
+            src.eval_terminal_cost()
+            J = src.get_J()
+        finally:
+            src.close()
+        self._ensure_engine().set_J(J)
+        self._invalidate()
+        self._pi = np.zeros(self.grid_sys.nodes_n, dtype=int)
 
 
 class PolicyEvaluator(DynamicProgramming):
