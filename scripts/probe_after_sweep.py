@@ -54,14 +54,14 @@ def spline(dims, udims, K=20):
 
 
 if __name__ == "__main__":
-    jobs = [
-        lambda: rollouts("pend_201", dict(CASES["pend_51x51x11"], x_grid_dim=[201, 201], u_grid_dim=[21]), 100, 131072, 1001, 10.0),
-        lambda: rollouts("cartpole_41", dict(CASES["cartpole_swingup"], x_grid_dim=[41] * 4, u_grid_dim=[11]), 10, 131072, 501, 5.0),
-        lambda: spline([501, 501], [51]),
-        lambda: spline([1001, 1001], [201], K=5),
-    ]
-    for job in jobs:
+    jobs = {
+        "rollout_pend": lambda: rollouts("pend_201", dict(CASES["pend_51x51x11"], x_grid_dim=[201, 201], u_grid_dim=[21]), 100, 131072, 1001, 10.0),
+        "rollout_cartpole": lambda: rollouts("cartpole_41", dict(CASES["cartpole_swingup"], x_grid_dim=[41] * 4, u_grid_dim=[11]), 10, 131072, 501, 5.0),
+        "spline501": lambda: spline([501, 501], [51]),
+        "spline1001": lambda: spline([1001, 1001], [201], K=5),
+    }
+    for name in (sys.argv[1:] or list(jobs)):
         try:
-            job()
+            jobs[name]()
         except Exception as e:   # keep going: every line is its own record
-            print(json.dumps({"error": repr(e)}), flush=True)
+            print(json.dumps({"job": name, "error": repr(e)}), flush=True)
