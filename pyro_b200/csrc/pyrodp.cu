@@ -749,13 +749,14 @@ extern "C" int pdp_set_interpolant(pdp_handle* h, int32_t which) {
     if (!h->S.coef) {
         for (int d = 0; d < 2; ++d) {
             const int m = P.dims[d];
-            std::vector<double> lev((size_t)m), knots, lu;
+            std::vector<double> lev((size_t)m), knots, lu, rden;
             CUDA_TRY(h, cudaMemcpy(lev.data(), P.level[d], (size_t)m * sizeof(double), cudaMemcpyDeviceToHost));
-            if (!spline_plan_axis(lev.data(), m, knots, lu))
+            if (!spline_plan_axis(lev.data(), m, knots, lu, rden))
                 return fail(h, PDP_ENOTSUP, "pdp_set_interpolant: a cubic spline needs at least 4 levels per axis");
             int rc;
             if ((rc = upload(h, knots.data(), knots.size(), &h->S.knots[d])) != PDP_OK) return rc;
             if ((rc = upload(h, lu.data(), lu.size(), &h->S.lu[d])) != PDP_OK) return rc;
+            if ((rc = upload(h, rden.data(), rden.size(), &h->S.rden[d])) != PDP_OK) return rc;
             h->S.m[d] = m;
         }
         void* c = nullptr;

@@ -22,6 +22,7 @@
 struct SplineDev {
     const double* knots[2];   // [m + 4] per axis
     const double* lu[2];      // [5][m] per axis: l1 (sub-diagonal), l2 (second sub-diagonal), d (diagonal of U), u1, u2
+    const double* rden[2];    // [m + 4][6] per axis: reciprocals of the six knot differences fpbspl divides by on interval l
     double* coef;             // [m0][m1] B-spline coefficients of J_next, rewritten before every sweep
     int m[2];
 };
@@ -42,6 +43,25 @@ __host__ __device__ inline void bspl3(const double* t, int l, double x, double h
     }
 }
 
+// The same recurrence with the six divisors of interval l tabulated as reciprocals (host, spline_plan_axis): twelve FP64
+// divisions per evaluation were half of the sweep kernel's instructions (ncu r02r).  One extra rounding per factor —
+// this path is floating-point parity anyway.
+__host__ __device__ inline void bspl3r(const double* t, const double* r6, int l, double x, double h[4]) {
+    double hh[3];
+    h[0] = 1.0;
+    int q = 0;
+    for (int j = 1; j <= 3; ++j) {
+        for (int i = 0; i < j; ++i) hh[i] = h[i];
+        h[0] = 0.0;
+        for (int i = 1; i <= j; ++i, ++q) {
+            const int li = l + i, lj = li - j;
+            const double f = hh[i - 1] * r6[q];
+            h[i - 1] = h[i - 1] + f * (t[li] - x);
+            h[i] = f * (x - t[lj]);
+        }
+    }
+}
+
 // fpbisp's interval search on the not-a-knot knot vector of m samples: 3 <= l <= m-1 with t[l] <= x < t[l+1]
 // (x already clamped to [t[3], t[m]]; the last interval is closed on the right)
 __host__ __device__ inline int spline_interval(const double* t, int m, double x, int guess) {
@@ -53,11 +73,17 @@ __host__ __device__ inline int spline_interval(const double* t, int m, double x,
 
 // Host side: knots and banded LU (kl = ku = 2, no pivoting) of the collocation matrix of one axis.  false when m < 4
 // (RectBivariateSpline needs more samples than the degree) or a pivot vanishes.
-inline bool spline_plan_axis(const double* x, int m, std::vector<double>& knots, std::vector<double>& lu) {
+inline bool spline_plan_axis(const double* x, int m, std::vector<double>& knots, std::vector<double>& lu, std::vector<double>& rden) {
     if (m < 4) return false;
     knots.assign((size_t)m + 4, 0.0);
     for (int j = 0; j < 4; ++j) { knots[j] = x[0]; knots[m + j] = x[m - 1]; }
     for (int j = 4; j < m; ++j) knots[j] = x[j - 2];
+    rden.assign(((size_t)m + 4) * 6, 0.0);
+    for (int l = 3; l <= m - 1; ++l) {
+        int q = 0;
+        for (int j = 1; j <= 3; ++j)
+            for (int i = 1; i <= j; ++i, ++q) rden[(size_t)l * 6 + q] = 1.0 / (knots[l + i] - knots[l + i - j]);
+    }
     // ab[i][c], c = j - i + 2 in 0..4
     std::vector<double> ab((size_t)m * 5, 0.0);
     for (int i = 0; i < m; ++i) {
@@ -152,7 +178,7 @@ __device__ __forceinline__ double spline_eval(const DevProblem& P, const SplineD
         if (arg > te) arg = te;
         const int cell = (int)((arg - tb) * P.inv_step[a]);   // level cell c -> knot interval c + 2 (3 for the first two cells)
         l[a] = spline_interval(t, m, arg, cell + 2);
-        bspl3(t, l[a], arg, w[a]);
+        bspl3r(t, S.rden[a] + 6 * l[a], l[a], arg, w[a]);
     }
     const double* __restrict__ c = S.coef + (long long)(l[0] - 3) * S.m[1] + (l[1] - 3);
     double sp = 0.0;

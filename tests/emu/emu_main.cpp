@@ -359,10 +359,10 @@ extern "C" int emu_spline_sweep(const pdp_problem* p, const double* J_next, cons
         fill(p, H);
         DevProblem& P = H.P;
         SplineDev S{};
-        std::vector<double> knots[2], lu[2], coef((size_t)P.dims[0] * P.dims[1]);
+        std::vector<double> knots[2], lu[2], rden[2], coef((size_t)P.dims[0] * P.dims[1]);
         for (int d = 0; d < 2; ++d) {
-            if (!spline_plan_axis(P.level[d], P.dims[d], knots[d], lu[d])) return -2;
-            S.knots[d] = knots[d].data(); S.lu[d] = lu[d].data(); S.m[d] = P.dims[d];
+            if (!spline_plan_axis(P.level[d], P.dims[d], knots[d], lu[d], rden[d])) return -2;
+            S.knots[d] = knots[d].data(); S.lu[d] = lu[d].data(); S.rden[d] = rden[d].data(); S.m[d] = P.dims[d];
         }
         S.coef = coef.data();
         emu_uint3 b128 = {128, 1, 1};
