@@ -593,6 +593,71 @@ def run_workload(ctx, args, wl_key, primary):
     return rec
 
 
+def after_the_sweep_records():
+    """N = 1 only, after the timed workloads: the two rows that sit next to the sweep — closed-loop
+    Euler rollout batches (pdp_rollout) and the bicubic-spline table sweep (pdp_set_interpolant) — each timed through the
+    public API and checked against its fixture of the unmodified reference (tests/golden/).  Never raises."""
+    out = {}
+    try:
+        from pyro_b200 import dynamicprogramming
+        from tests.cases import CASES, build_case
+        golden = lambda name: np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+        # ---- rollouts: parity on the fixture's grid, throughput on a 201 x 201 x 21 policy --------------------------------
+        gold = golden("rollout_pend_51x51x11")
+        _, grid, cf = build_case(CASES["pend_51x51x11"])
+        dp = dynamicprogramming.DynamicProgrammingWithLookUpTable(grid, cf)
+        dp.verbose = False
+        dp.compute_steps(int(gold["sweeps"]))
+        npts, tf = int(gold["npts"]), float(gold["tf"])
+        _, x, u = dp.compute_closed_loop_trajectories(gold["x0"], tf, npts)
+        rec = {"parity": {"against": "tests/golden/rollout_pend_51x51x11.npz: (ctl + sys).compute_trajectory(tf, n, 'euler') of the unmodified reference",
+                          "policy_equal": bool(np.array_equal(dp.pi, gold["pi"])),
+                          "x_Linf_error": float(np.abs(x - gold["x"]).max()), "u_Linf_error": float(np.abs(u - gold["u"]).max())}}
+        sys_, grid, cf = build_case(dict(CASES["pend_51x51x11"], x_grid_dim=[201, 201], u_grid_dim=[21]))
+        dp = dynamicprogramming.DynamicProgrammingWithLookUpTable(grid, cf)
+        dp.verbose = False
+        dp.compute_steps(100)
+        B, npts = 131072, 1001
+        x0 = np.random.default_rng(1).uniform(np.asarray(sys_.x_lb) * 0.9, np.asarray(sys_.x_ub) * 0.9, (B, 2))
+        dp.compute_closed_loop_trajectories(x0[:1024], 10.0, npts, stride=100)
+        t0 = time.perf_counter()
+        dp.compute_closed_loop_trajectories(x0, 10.0, npts, stride=100)
+        wall = time.perf_counter() - t0
+        rec.update({"workload": "SinglePendulum 201 x 201 x 21 policy after 100 sweeps, 131072 trajectories x 1001 points (tf = 10), every 100th point copied back",
+                    "wall_s": wall, "value": B * (npts - 1) / wall, "unit": "trajectory steps/s", "timing": "host wall clock around the C-ABI call incl. copies"})
+        out["rollout_batches"] = rec
+    except Exception as exc:
+        out["rollout_batches"] = {"error": f"{type(exc).__name__}: {exc}"}
+    try:
+        from pyro_b200 import dynamicprogramming
+        from tests.cases import CASES, build_case
+        golden = lambda name: np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+        # ---- spline class: parity on the fixture, time per backup on the cfg2 grid ---------------------------------------
+        gold = golden("spline_pend_51x51x11")
+        _, grid, cf = build_case(CASES["pend_51x51x11"])
+        dp = dynamicprogramming.DynamicProgramming2DRectBivariateSpline(grid, cf)
+        dp.verbose = False
+        k = int(gold["snapshots"][1])
+        dp.compute_steps(k)
+        J_ref = gold[f"J_{k}"]
+        rec = {"parity": {"against": "tests/golden/spline_pend_51x51x11.npz: DynamicProgramming2DRectBivariateSpline of the unmodified reference",
+                          "sweeps": k, "J_Linf_error": float(np.abs(dp.J - J_ref).max() / np.abs(J_ref).max()),
+                          "pi_mismatches": int((dp.pi != gold[f"pi_{k}"]).sum())}}
+        _, grid, cf = build_case(WORKLOADS["cfg2"])
+        dp = dynamicprogramming.DynamicProgramming2DRectBivariateSpline(grid, cf)
+        eng, K = dp._engine, 5
+        eng.sweep(2)
+        eng.sweep(K)
+        ms = eng.last_sweep_ms / K
+        rec.update({"workload": "SinglePendulum 1001 x 1001 x 201 in table mode (tables from pdp_build_tables), spline refitted every backup",
+                    "ms_per_backup": ms, "value": float(grid.nodes_n) * grid.actions_n / ms * 1e3, "unit": "evals/s", "kernel": eng.kernel_info,
+                    "timing": "CUDA events inside pdp_sweep: two fit kernels + the sweep kernel per backup"})
+        out["spline_class"] = rec
+    except Exception as exc:
+        out["spline_class"] = {"error": f"{type(exc).__name__}: {exc}"}
+    return out
+
+
 def main():
     if len(sys.argv) >= 3 and sys.argv[1] == "--clock-sampler":
         return clock_sampler_main(int(sys.argv[2]), float(sys.argv[3]) if len(sys.argv) > 3 else 0.002)
@@ -607,6 +672,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-after", action="store_true", help="skip the rollout / spline records (SURVEY.md 8f rank 4)")
     ap.add_argument("--no-extra", action="store_true", help="reference arm: skip the cfg1 LUT / base-class measurements")
     args = ap.parse_args()
     wl_name = f"{WORKLOAD_NAMES[args.workload]} (BASELINE {args.workload})"
@@ -629,6 +695,8 @@ def main():
                 subs[key] = {"error": f"{type(exc).__name__}: {exc}"}
     if ctx.rank == 0:
         line["sub_records"] = subs
+        if ctx.world == 1 and not args.no_after:
+            line["after_the_sweep"] = after_the_sweep_records()
         print(json.dumps(line), flush=True)
     if ctx.world > 1:
         ctx.dist.barrier()
