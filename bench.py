@@ -593,7 +593,7 @@ def run_workload(ctx, args, wl_key, primary):
     return rec
 
 
-def after_the_sweep_records():
+def after_the_sweep_records(n_traj=131072, policy_dims=(201, 201), policy_sweeps=100, spline_case=None):
     """N = 1 only, after the timed workloads: the two rows that sit next to the sweep — closed-loop
     Euler rollout batches (pdp_rollout) and the bicubic-spline table sweep (pdp_set_interpolant) — each timed through the
     public API and checked against its fixture of the unmodified reference (tests/golden/).  Never raises."""
@@ -613,17 +613,18 @@ def after_the_sweep_records():
         rec = {"parity": {"against": "tests/golden/rollout_pend_51x51x11.npz: (ctl + sys).compute_trajectory(tf, n, 'euler') of the unmodified reference",
                           "policy_equal": bool(np.array_equal(dp.pi, gold["pi"])),
                           "x_Linf_error": float(np.abs(x - gold["x"]).max()), "u_Linf_error": float(np.abs(u - gold["u"]).max())}}
-        sys_, grid, cf = build_case(dict(CASES["pend_51x51x11"], x_grid_dim=[201, 201], u_grid_dim=[21]))
+        sys_, grid, cf = build_case(dict(CASES["pend_51x51x11"], x_grid_dim=list(policy_dims), u_grid_dim=[21]))
         dp = dynamicprogramming.DynamicProgrammingWithLookUpTable(grid, cf)
         dp.verbose = False
-        dp.compute_steps(100)
-        B, npts = 131072, 1001
+        dp.compute_steps(policy_sweeps)
+        B, npts = int(n_traj), 1001
         x0 = np.random.default_rng(1).uniform(np.asarray(sys_.x_lb) * 0.9, np.asarray(sys_.x_ub) * 0.9, (B, 2))
-        dp.compute_closed_loop_trajectories(x0[:1024], 10.0, npts, stride=100)
+        dp.compute_closed_loop_trajectories(x0[:min(B, 1024)], 10.0, npts, stride=100)
         t0 = time.perf_counter()
         dp.compute_closed_loop_trajectories(x0, 10.0, npts, stride=100)
         wall = time.perf_counter() - t0
-        rec.update({"workload": "SinglePendulum 201 x 201 x 21 policy after 100 sweeps, 131072 trajectories x 1001 points (tf = 10), every 100th point copied back",
+        rec.update({"workload": f"SinglePendulum {policy_dims[0]} x {policy_dims[1]} x 21 policy after {policy_sweeps} sweeps, {B} trajectories x {npts} points "
+                                "(tf = 10), every 100th point copied back",
                     "wall_s": wall, "value": B * (npts - 1) / wall, "unit": "trajectory steps/s", "timing": "host wall clock around the C-ABI call incl. copies"})
         out["rollout_batches"] = rec
     except Exception as exc:
@@ -643,13 +644,14 @@ def after_the_sweep_records():
         rec = {"parity": {"against": "tests/golden/spline_pend_51x51x11.npz: DynamicProgramming2DRectBivariateSpline of the unmodified reference",
                           "sweeps": k, "J_Linf_error": float(np.abs(dp.J - J_ref).max() / np.abs(J_ref).max()),
                           "pi_mismatches": int((dp.pi != gold[f"pi_{k}"]).sum())}}
-        _, grid, cf = build_case(WORKLOADS["cfg2"])
+        case = spline_case or WORKLOADS["cfg2"]
+        _, grid, cf = build_case(case)
         dp = dynamicprogramming.DynamicProgramming2DRectBivariateSpline(grid, cf)
         eng, K = dp._engine, 5
         eng.sweep(2)
         eng.sweep(K)
         ms = eng.last_sweep_ms / K
-        rec.update({"workload": "SinglePendulum 1001 x 1001 x 201 in table mode (tables from pdp_build_tables), spline refitted every backup",
+        rec.update({"workload": f"SinglePendulum {case['x_grid_dim']} x {case['u_grid_dim']} in table mode (tables from pdp_build_tables), spline refitted every backup",
                     "ms_per_backup": ms, "value": float(grid.nodes_n) * grid.actions_n / ms * 1e3, "unit": "evals/s", "kernel": eng.kernel_info,
                     "timing": "CUDA events inside pdp_sweep: two fit kernels + the sweep kernel per backup"})
         out["spline_class"] = rec
