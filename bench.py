@@ -552,6 +552,9 @@ def run_workload(ctx, args, wl_key, primary):
                              "so this fraction can exceed 1 and is not a bandwidth statement"},
         "note": "counters per launch come from the committed ncu capture of the same kernel and workload (profiles/traffic.json); "
                 "time, clock and therefore every rate and fraction are this run's",
+        "bound_note": ("fp64_issue = FP64 warp instructions per second over the measured 2.0 / clk / SM; the FP64 unit is a pipe shared by the "
+                       "SM's four sub-partitions, and the r02p A/B (11 % fewer non-FP64 instructions, same sweep time) shows that pipe, not the "
+                       "issue port, binds the 2-D kernel") if bound == "fp64_issue" else None,
     }
 
     # ---- CPU baseline beside it (rank 0, N=1, primary workload only) -----------------------------------------

@@ -1468,6 +1468,10 @@ extern "C" int pdp_rollout(pdp_handle* h, const double* phys, const double* x0_h
     if (e == cudaSuccess && du) e = cudaMemcpyAsync(u_out_host, du, (size_t)keep * m * B * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     cudaFree(dphys); cudaFree(dx0); cudaFree(dx); cudaFree(du);
+    if (e == cudaErrorMemoryAllocation) {   // a batch that does not fit is the caller's argument, not a broken handle
+        cudaGetLastError();
+        return fail(h, PDP_EINVAL, "pdp_rollout: the kept points (n_keep x (n + m) x B doubles) do not fit the device memory; use a larger stride or fewer trajectories");
+    }
     if (e != cudaSuccess) return fail(h, PDP_ECUDA, std::string("pdp_rollout: ") + cudaGetErrorString(e));
     return PDP_OK;
 }
