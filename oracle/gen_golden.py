@@ -145,6 +145,31 @@ def main_spline():
         print(f"spline_{name}: snapshots={snaps} J_max={dp.J.max():.6f} J_min={dp.J.min():.6f} -> {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def main_3d_example():
+    """Fixture of a 3-D example of the reference (helicopter_tunnel.py, obstacles in isavalidstate) on a coarse grid: the
+    reference's own tables (x_next_table, G) and J / pi snapshots of DynamicProgrammingWithLookUpTable, alpha = 0.999."""
+    ns = ref_loader.load()
+    from pyro.dynamic import drone
+    from tests.cases import helicopter_tunnel_example
+    snaps = [1, 5, 25]
+    with ref_loader.quiet():
+        sys_, grid, qcf = helicopter_tunnel_example(drone, ns.costfunction, ns.discretizer)
+        dp = ns.dynamicprogramming.DynamicProgrammingWithLookUpTable(grid, qcf)
+        dp.alpha = 0.999
+        out = {"J0": dp.J.copy(), "x_next_table": grid.x_next_table.copy(), "G": dp.G.copy(), "x_next_isok": grid.x_next_isok.copy()}
+        k = 0
+        for target in snaps:
+            dp.compute_steps(target - k)
+            k = target
+            out[f"J_{k}"] = dp.J.copy()
+            out[f"pi_{k}"] = dp.pi.astype(np.int64)
+    path = os.path.join(OUT, "helicopter_tunnel_15x13x11.npz")
+    np.savez_compressed(path, snapshots=np.array(snaps), x_grid_dim=np.array(grid.x_grid_dim), u_grid_dim=np.array(grid.u_grid_dim),
+                        alpha=0.999, **out)
+    print(f"helicopter_tunnel: N={grid.nodes_n} A={grid.actions_n} invalid arrivals {1 - grid.x_next_isok.mean():.3f} "
+          f"J_max={dp.J.max():.3f} -> {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 if __name__ == "__main__":
     if "--rollouts-only" in sys.argv:
         main_rollouts()
@@ -152,8 +177,12 @@ if __name__ == "__main__":
     if "--spline-only" in sys.argv:
         main_spline()
         sys.exit(0)
+    if "--3d-only" in sys.argv:
+        main_3d_example()
+        sys.exit(0)
     if "--policy-only" not in sys.argv:
         main()
     main_policy()
     main_rollouts()
     main_spline()
+    main_3d_example()

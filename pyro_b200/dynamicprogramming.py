@@ -145,7 +145,7 @@ class DynamicProgramming:
 
     def _make_engine(self, P):
         if self._engine_factory is not None:
-            return self._engine_factory(self, P)
+            return self._make_lut_engine(P) if P.system_id == _lib.PDP_SYS_LUT else self._engine_factory(self, P)
         if self.shard:
             # one process per GPU (torchrun): opt-in, because every rank must then build and drive the same planner —
             # get_J / get_pi / parameter changes become collectives
@@ -184,7 +184,7 @@ class DynamicProgramming:
     _invalid_input_is_exact_inf = True
 
     def _make_lut_engine(self, P):
-        eng = Engine(P)
+        eng = self._engine_factory(self, P) if self._engine_factory is not None else Engine(P)
         x_next, G = build_lookup_tables(self.grid_sys, self.cf, self.t if self.time_varying else self.tf,
                                         exact_inf=self._invalid_input_is_exact_inf, use_grid_tables=not self.time_varying)
         eng.set_lut(x_next, G)

@@ -122,3 +122,24 @@ def oracle_objects(case):
         if key in case:
             setattr(cost, key, case[key])
     return grid, cost
+
+
+def helicopter_tunnel_example(drone, costfunction, discretizer, x_grid_dim=(15, 13, 11), u_grid_dim=(5,)):
+    """examples/demos_by_tool/dynamicprogramming/helicopter_tunnel.py of the reference on the given pyro modules (the real
+    ones: the 3-D example systems live in pyro.dynamic, not in the mirrors), with a coarser grid: a 3-state plant whose
+    isavalidstate holds obstacles, i.e. a table-mode problem.  -> (sys, grid_sys with look-up tables, cost function)."""
+    sys_ = drone.ConstantSpeedHelicopterTunnel()
+    sys_.obstacles = [[(2, 2), (4, 4)], [(8, 5), (10, 10)], [(14, 0), (16, 4)]]
+    sys_.mass, sys_.vx, sys_.width = 0.1, 5.0, 1.0
+    sys_.x_ub = np.array([+60, 10, +20])
+    sys_.x_lb = np.array([-60, 0, +0])
+    sys_.u_ub = np.array([+20])
+    sys_.u_lb = np.array([-20])
+    grid = discretizer.GridDynamicSystem(sys_, tuple(x_grid_dim), list(u_grid_dim), 0.05)
+    qcf = costfunction.QuadraticCostFunctionWithDomainCheck.from_sys(sys_)
+    qcf.xbar = np.array([0.0, 2.0, 20])
+    qcf.INF, qcf.EPS = 100000, 0.2
+    qcf.Q[0, 0], qcf.Q[1, 1], qcf.Q[2, 2] = 2.0, 200.0, 0.0
+    qcf.R[0, 0] = 5.0
+    qcf.S[0, 0], qcf.S[1, 1], qcf.S[2, 2] = 20.0, 50.0, 0.0
+    return sys_, grid, qcf

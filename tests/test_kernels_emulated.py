@@ -419,3 +419,105 @@ def test_spline_mirror_class_drives_a_table_mode_engine():
     _, grid4, cf4 = build_case(CASES["twolink_9"])
     with pytest.raises(NotImplementedError):
         dynamicprogramming.DynamicProgramming2DRectBivariateSpline(grid4, cf4, engine_factory=lambda dp, P: EmuSplineEngine(P))
+
+
+# ---- a 3-D example of the reference (obstacles in isavalidstate): table mode, n = 3 -----------------------------------
+class EmuLutEngine:
+    """Engine interface of a table-mode handle backed by the emulated sweep_lut_kernel (host-logic tests without a GPU)."""
+    kernel_info = "sweep_lut_kernel (emulated)"
+
+    def __init__(self, P):
+        self.problem, self.N, self.launch_count = P, P.N, 0
+        self.J = self.J_next = self.pi = None
+
+    def set_lut(self, x_next, G):
+        self.x_next, self.G = np.array(x_next, dtype=float), np.array(G, dtype=float)
+
+    def set_J(self, J):
+        self.J = np.array(J, dtype=float)
+
+    def get_J(self):
+        return self.J.copy()
+
+    def get_J_next(self):
+        return self.J_next.copy()
+
+    def get_pi(self):
+        return self.pi.copy()
+
+    def sweep(self, n=1):
+        out = np.empty((n, 3))
+        for k in range(n):
+            self.J_next = self.J
+            self.J, self.pi, out[k] = emu.lut_sweep(self.problem, self.J_next, self.x_next, self.G)
+            self.launch_count += 1
+        return out
+
+    def get_input_from_policy(self, k):
+        U = np.stack([g.reshape(-1) for g in np.meshgrid(*[self.problem.tables[f"u_level{i}"] for i in range(self.problem.m)],
+                                                         indexing="ij")], axis=1)
+        return U[self.pi, k]
+
+    def close(self):
+        pass
+
+
+def test_emulated_lut_kernel_on_the_tables_of_a_3d_reference_example():
+    """sweep_lut_kernel<3, G> on the reference's own x_next_table / G of helicopter_tunnel.py (coarse grid): J and pi of the
+    reference's DynamicProgrammingWithLookUpTable bit for bit (fixture only; no reference import)."""
+    gold = load_golden("helicopter_tunnel_15x13x11")
+    dims, udims = [int(d) for d in gold["x_grid_dim"]], [int(d) for d in gold["u_grid_dim"]]
+    lb, ub = [-60.0, 0.0, 0.0], [60.0, 10.0, 20.0]
+
+    class Sys3:
+        n, m = 3, 1
+        x_lb, x_ub, u_lb, u_ub = np.array(lb), np.array(ub), np.array([-20.0]), np.array([20.0])
+
+    class Grid3:
+        sys, dt = Sys3(), 0.05
+        x_grid_dim, u_grid_dim = np.array(dims), np.array(udims)
+        x_level = [np.linspace(lb[i], ub[i], dims[i]) for i in range(3)]
+        u_level = [np.linspace(-20.0, 20.0, udims[0])]
+
+    class Cost3:
+        INF = 100000
+    P = problem.extract(Grid3(), Cost3(), float(gold["alpha"]))
+    assert P.system_id == 0
+    J, k = gold["J0"], 0
+    for target in gold["snapshots"]:
+        while k < target:
+            J, pi, _ = emu.lut_sweep(P, J, gold["x_next_table"], gold["G"])
+            k += 1
+        assert np.array_equal(J, gold[f"J_{k}"]) and np.array_equal(pi, gold[f"pi_{k}"]), k
+
+
+def test_mirror_planner_drops_in_on_the_real_pyro_objects_of_a_3d_example():
+    """The reference's helicopter_tunnel.py with only the planner class swapped: real pyro system (obstacles), real
+    GridDynamicSystem with its tables, real QuadraticCostFunctionWithDomainCheck -> the mirror selects table mode, builds
+    G with the table class's INF semantics and reproduces the reference's J / pi; the controller it hands out is pyro's."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("unmodified reference not present")
+    from pyro_b200 import dynamicprogramming
+    from tests.cases import helicopter_tunnel_example
+    ns = ref_loader.load()
+    from pyro.dynamic import drone
+    gold = load_golden("helicopter_tunnel_15x13x11")
+    with ref_loader.quiet():
+        sys_, grid, qcf = helicopter_tunnel_example(drone, ns.costfunction, ns.discretizer)
+    dp = dynamicprogramming.DynamicProgrammingWithLookUpTable(grid, qcf, engine_factory=lambda dp, P: EmuLutEngine(P))
+    dp.alpha, dp.verbose = float(gold["alpha"]), False
+    assert dp._engine.problem.system_id == 0                      # obstacles in isavalidstate: table mode
+    assert np.array_equal(dp.J, gold["J0"])
+    assert np.array_equal(dp._engine.G, gold["G"]) and np.array_equal(dp._engine.x_next, gold["x_next_table"])
+    k = 0
+    for target in gold["snapshots"]:
+        dp.compute_steps(int(target) - k)
+        k = int(target)
+        assert np.array_equal(dp.J, gold[f"J_{k}"]) and np.array_equal(dp.pi, gold[f"pi_{k}"]), k
+    ctl = dp.get_lookup_table_controller()
+    assert type(ctl).__mro__[1].__name__ == "LookUpTableController" and type(ctl).__mro__[1].__module__.startswith("pyro.")
+    x = np.array([1.0, 6.0, 5.0])
+    with ref_loader.quiet():
+        ref = ns.dynamicprogramming.LookUpTableController(grid, gold[f"pi_{k}"])
+    assert np.array_equal(ctl.c(x, 0), ref.c(x, 0))

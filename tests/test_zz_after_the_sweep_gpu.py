@@ -110,3 +110,27 @@ def test_spline_interpolant_argument_errors():
     _, grid4, cf4 = build_case(CASES["twolink_9"])
     with pytest.raises(NotImplementedError):
         dynamicprogramming.DynamicProgramming2DRectBivariateSpline(grid4, cf4)
+
+
+# ---- a 3-D example of the reference on the device (table mode, n = 3) ----------------------------------------------------
+def test_reference_3d_example_drops_in_with_real_pyro_objects():
+    """examples/demos_by_tool/dynamicprogramming/helicopter_tunnel.py (coarse grid) with only the planner class swapped:
+    the REAL pyro plant (obstacles in isavalidstate), grid with its look-up tables and cost function from the unmodified
+    reference under baseline/_ref -> table-mode handle, sweep_lut_kernel<3> -> J / pi of the reference bit for bit."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("unmodified reference not present (baseline/_ref)")
+    from tests.cases import helicopter_tunnel_example
+    ns = ref_loader.load()
+    from pyro.dynamic import drone
+    gold = load_golden("helicopter_tunnel_15x13x11")
+    with ref_loader.quiet():
+        sys_, grid, qcf = helicopter_tunnel_example(drone, ns.costfunction, ns.discretizer)
+    dp = dynamicprogramming.DynamicProgrammingWithLookUpTable(grid, qcf)
+    dp.alpha, dp.verbose = float(gold["alpha"]), False
+    assert "sweep_lut_kernel" in dp._engine.kernel_info and np.array_equal(dp.J, gold["J0"])
+    k = 0
+    for target in gold["snapshots"]:
+        dp.compute_steps(int(target) - k)
+        k = int(target)
+        assert np.array_equal(dp.J, gold[f"J_{k}"]) and np.array_equal(dp.pi, gold[f"pi_{k}"]), k
