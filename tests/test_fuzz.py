@@ -1,0 +1,125 @@
+"""Randomised parity (seeded, deterministic): random plants / bounds / grids / action ladders / costs / discounts.
+
+  * the product's kernels (compiled for the CPU emulator) against the C oracle: every lane split, both MONO loops of the
+    pendulum kernel, the order-agnostic and the range-skipping 4-D kernels, the fused dJ statistics — bit for bit;
+  * the C oracle against the LIVE unmodified reference (where it is importable: this container) after 1-3 sweeps of its
+    DynamicProgrammingWithLookUpTable — bit for bit.  This widens the pin of the oracle beyond the committed fixtures.
+
+`python tests/test_fuzz.py kernels|reference <first seed> <count>` runs longer campaigns (DESIGN.md section 3 records one:
+3000 + 3000 cases, no mismatch)."""
+import sys
+
+import numpy as np
+import pytest
+
+SYSTEMS = ["SinglePendulum", "SinglePendulum", "CartPole", "TwoLinkManipulator", "DoublePendulum"]
+
+
+def random_case(rng, tiny=False):
+    kind = str(rng.choice(SYSTEMS))
+    case = dict(system=kind, INF=float(rng.choice([300.0, 1000.0, 50.0])))
+    if kind == "SinglePendulum":
+        n, m = 2, 1
+        case["x_grid_dim"] = [int(rng.integers(2, 14 if tiny else 40)), int(rng.integers(2, 30 if tiny else 200))]
+        case["u_grid_dim"] = [int(rng.integers(1, 12 if tiny else 70))]
+        if rng.random() < 0.5:
+            case["sys_params"] = {"d1": float(rng.uniform(0, 1))}
+    else:
+        n, m = 4, (1 if kind == "CartPole" else 2)
+        hi = (5, 5, 6, 7) if tiny else (8, 8, 14, 20)
+        case["x_grid_dim"] = [int(rng.integers(2, h)) for h in hi]
+        case["u_grid_dim"] = [int(rng.integers(1, 5 if tiny else 12)) for _ in range(m)]
+    lo, hi = -rng.uniform(0.3, 7.0, n), rng.uniform(0.3, 7.0, n)
+    if rng.random() < 0.3:
+        shift = rng.uniform(-2, 2, n)
+        lo, hi = lo + shift, hi + shift
+    case["x_lb"], case["x_ub"] = lo.tolist(), hi.tolist()
+    ul = rng.uniform(0.5, 15.0, m)
+    case["u_lb"], case["u_ub"] = (-ul).tolist(), (ul * rng.uniform(0.5, 1.0, m)).tolist()
+    case["dt"] = float(rng.choice([0.05, 0.1, 0.02, 0.2]))
+    case["xbar"] = rng.uniform(lo, hi).tolist()
+    case["cost"] = str(rng.choice(["quadratic", "quadratic", "time", "reach", "domaincheck"]))
+    if case["cost"] in ("quadratic", "domaincheck"):
+        case["Q"], case["R"] = rng.uniform(0, 3, n).tolist(), rng.uniform(0.01, 2, m).tolist()
+    case["EPS"] = float(rng.choice([1e-3, 0.5, 1.0]))
+    case["alpha"] = float(rng.choice([1.0, 1.0, 0.9, 0.5]))
+    return case
+
+
+def kernels_vs_oracle(seed):
+    """Mismatch descriptions of one random case (empty list = parity)."""
+    from oracle import c_oracle
+    from pyro_b200 import problem
+    from tests.cases import build_case
+    from tests.emu import emu
+    rng = np.random.default_rng(seed)
+    case = random_case(rng)
+    _, grid, cf = build_case(case)
+    P = problem.extract(grid, cf, case["alpha"])
+    assert P.system_id != 0, case
+    J0 = rng.uniform(0, case["INF"], P.N) if rng.random() < 0.8 else c_oracle.terminal(P)
+    Jr, pr = c_oracle.sweep_fused(P, J0)
+    variants = [(1, False, None)] + ([(4, False, None)] if P.A >= 4 else []) + ([(16, False, None)] if P.A >= 16 else [])
+    if case["system"] == "SinglePendulum":
+        variants += [(1, 2, None), (1, True, None)] + ([(4, 2, None)] if P.A >= 4 else [])   # loop nest, order-agnostic loop
+    else:
+        variants += [(1, False, "generic")]
+    bad = []
+    for lanes, loop, mech2 in variants:
+        J, pi, st = emu.sweep(P, J0, lanes=lanes, force_generic=loop, mech2=mech2)
+        d = J - J0
+        if not (np.array_equal(J, Jr) and np.array_equal(pi, pr) and st[0] == J.max() and st[1] == d.max() and st[2] == d.min()):
+            bad.append((seed, lanes, loop, mech2, int((J != Jr).sum()), int((pi != pr).sum()), case))
+    return bad
+
+
+def oracle_vs_reference(ns, seed):
+    from oracle import c_oracle, ref_loader
+    from pyro_b200 import problem
+    from tests.cases import build_case
+    rng = np.random.default_rng(seed)
+    case = random_case(rng, tiny=True)
+    k = int(rng.integers(1, 4))
+    with ref_loader.quiet():
+        _, _, _, rdp = ref_loader.build_reference(ns, case)
+        rdp.compute_steps(k)
+    _, grid, cf = build_case(case)
+    P = problem.extract(grid, cf, case["alpha"])
+    assert P.system_id != 0, case
+    J, pi, _ = c_oracle.run(P, k)
+    if np.array_equal(J, rdp.J) and np.array_equal(pi, rdp.pi):
+        return []
+    return [(seed, k, int((J != rdp.J).sum()), int((pi != rdp.pi).sum()), case)]
+
+
+@pytest.mark.filterwarnings("ignore::RuntimeWarning")
+def test_random_problems_emulated_kernels_equal_c_oracle():
+    bad = [b for seed in range(100, 220) for b in kernels_vs_oracle(seed)]
+    assert not bad, bad[:3]
+
+
+@pytest.mark.filterwarnings("ignore::RuntimeWarning", "ignore::DeprecationWarning")
+def test_random_problems_c_oracle_equals_the_live_reference():
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("unmodified reference not present")
+    ns = ref_loader.load()
+    bad = [b for seed in range(7000, 7150) for b in oracle_vs_reference(ns, seed)]
+    assert not bad, bad[:3]
+
+
+if __name__ == "__main__":
+    import os
+    import warnings
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    warnings.simplefilter("ignore")
+    which, first, count = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+    if which == "reference":
+        from oracle import ref_loader
+        ns = ref_loader.load()
+    bad = []
+    for seed in range(first, first + count):
+        bad += kernels_vs_oracle(seed) if which == "kernels" else oracle_vs_reference(ns, seed)
+    print(f"{which}: seeds {first}..{first + count - 1}: {len(bad)} mismatching variants")
+    for b in bad[:10]:
+        print(b)
