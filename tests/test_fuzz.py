@@ -5,7 +5,7 @@
   * the C oracle against the LIVE unmodified reference (where it is importable: this container) after 1-3 sweeps of its
     DynamicProgrammingWithLookUpTable — bit for bit.  This widens the pin of the oracle beyond the committed fixtures.
 
-`python tests/test_fuzz.py kernels|reference <first seed> <count>` runs longer campaigns (DESIGN.md section 3 records one:
+`python tests/test_fuzz.py kernels|reference|halo <first seed> <count>` runs longer campaigns (DESIGN.md section 3 records one:
 3000 + 3000 cases, no mismatch)."""
 import sys
 
@@ -108,6 +108,47 @@ def test_random_problems_c_oracle_equals_the_live_reference():
     assert not bad, bad[:3]
 
 
+def halo_sufficiency(seed):
+    """One random case cut into random slabs over axis 0: every slab's launch sees J_next only on slab + the halo that
+    pdp_compute_halo promises (NaN elsewhere) and must reproduce the whole-grid backup."""
+    import ctypes as C
+    from pyro_b200 import _lib, problem
+    from tests.cases import build_case
+    from tests.emu import emu
+    rng = np.random.default_rng(seed)
+    case = random_case(rng)
+    n0 = int(rng.integers(6, 40))
+    case["x_grid_dim"] = [n0] + ([int(rng.integers(2, 60))] if case["system"] == "SinglePendulum"
+                                 else [int(rng.integers(2, 5)), int(rng.integers(2, 8)), int(rng.integers(2, 10))])
+    if rng.random() < 0.5:          # velocity bounds small against the position range: thin halos, many slabs
+        k = 1 if case["system"] == "SinglePendulum" else 2
+        case["x_lb"][k], case["x_ub"][k] = -float(rng.uniform(0.2, 1.5)), float(rng.uniform(0.2, 1.5))
+    _, grid, cf = build_case(case)
+    P = problem.extract(grid, cf, case["alpha"])
+    lo, hi = C.c_int32(), C.c_int32()
+    _lib.check(_lib.load().pdp_compute_halo(C.byref(P.c), C.byref(lo), C.byref(hi)))
+    lo, hi = lo.value, hi.value
+    plane = P.N // n0
+    J0 = rng.uniform(0, case["INF"], P.N)
+    J_ref, pi_ref, _ = emu.sweep(P, J0, lanes=1)
+    cuts = sorted(set([0, n0] + [int(c) for c in rng.integers(1, n0, int(rng.integers(1, 5)))]))
+    J, pi = np.full(P.N, -1.0), np.full(P.N, -1, dtype=np.int64)
+    for b, e in zip(cuts[:-1], cuts[1:]):
+        seen = np.full(P.N, np.nan)
+        a0, a1 = max(0, b - lo), min(n0, e + hi)
+        seen[a0 * plane:a1 * plane] = J0[a0 * plane:a1 * plane]
+        emu.sweep_planes(P, seen, J, pi, b, e, lanes=1)
+    if np.array_equal(J, J_ref) and np.array_equal(pi, pi_ref):
+        return []
+    return [(seed, lo, hi, cuts, int((J != J_ref).sum()), int(np.isnan(J).sum()), case)]
+
+
+@pytest.mark.filterwarnings("ignore::RuntimeWarning")
+def test_random_slab_layouts_need_only_the_promised_halo():
+    bad = [b for seed in range(300, 380) for b in halo_sufficiency(seed)]
+    assert not bad, bad[:3]
+
+
 if __name__ == "__main__":
     import os
     import warnings
@@ -119,7 +160,7 @@ if __name__ == "__main__":
         ns = ref_loader.load()
     bad = []
     for seed in range(first, first + count):
-        bad += kernels_vs_oracle(seed) if which == "kernels" else oracle_vs_reference(ns, seed)
+        bad += kernels_vs_oracle(seed) if which == "kernels" else halo_sufficiency(seed) if which == "halo" else oracle_vs_reference(ns, seed)
     print(f"{which}: seeds {first}..{first + count - 1}: {len(bad)} mismatching variants")
     for b in bad[:10]:
         print(b)
