@@ -28,6 +28,8 @@ def load():
         _lib.emu_lut_sweep.argtypes = [C.c_void_p] * 7 + [C.c_int]
         _lib.emu_mech2_evals.restype = C.c_longlong
         _lib.emu_mech2_evals.argtypes = [C.c_int]
+        _lib.emu_build_tables.restype = C.c_int
+        _lib.emu_build_tables.argtypes = [C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.emu_spline_sweep.restype = C.c_int
         _lib.emu_spline_sweep.argtypes = [C.c_void_p] * 7 + [C.c_int, C.c_void_p]
         _lib.emu_rollout.restype = C.c_int
@@ -131,3 +133,15 @@ def spline_sweep(problem, J_next, x_next, G, grid_blocks=24):
     if rc != 0:
         raise RuntimeError(f"emu_spline_sweep failed ({rc})")
     return J, pi, stats, coef
+
+
+def build_tables(problem, node_begin=0, count=None):
+    """build_tables_kernel (pdp_build_tables) on the CPU: (x_next (K,A,n), x_next_isok (K,A) bool, G (K,A))."""
+    count = problem.N - node_begin if count is None else count
+    xn = np.empty((count, problem.A, problem.n))
+    ok = np.empty((count, problem.A), dtype=np.uint8)
+    G = np.empty((count, problem.A))
+    rc = load().emu_build_tables(C.addressof(problem.c), int(node_begin), int(count), xn.ctypes.data, ok.ctypes.data, G.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"emu_build_tables failed ({rc})")
+    return xn, ok.astype(bool), G

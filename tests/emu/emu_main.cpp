@@ -385,3 +385,24 @@ extern "C" int emu_spline_sweep(const pdp_problem* p, const double* J_next, cons
         return -3;
     }
 }
+
+// pdp_build_tables' kernel: the reference's dense tables of nodes [node0, node0 + count) of a fused system
+extern "C" int emu_build_tables(const pdp_problem* p, long long node0, long long count, double* x_next, unsigned char* x_ok, double* G) {
+    if (!p || p->system_id == PDP_SYS_LUT) return -1;
+    try {
+        HostProblem H;
+        fill(p, H);
+        DevProblem& P = H.P;
+        std::vector<unsigned char> act_ok(p->act_ok, p->act_ok + P.A);
+        P.act_ok = act_ok.data();
+        const long long pairs = count * P.A;
+        emu_uint3 grid = {(unsigned)((pairs + 255) / 256), 1, 1}, block = {256, 1, 1};
+        emu_launch(grid, block, [&]() {
+            if (P.n == 2) build_tables_kernel<2>(P, node0, count, x_next, x_ok, G);
+            else build_tables_kernel<4>(P, node0, count, x_next, x_ok, G);
+        });
+        return 0;
+    } catch (const std::exception&) {
+        return -3;
+    }
+}

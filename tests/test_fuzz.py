@@ -5,7 +5,7 @@
   * the C oracle against the LIVE unmodified reference (where it is importable: this container) after 1-3 sweeps of its
     DynamicProgrammingWithLookUpTable — bit for bit.  This widens the pin of the oracle beyond the committed fixtures.
 
-`python tests/test_fuzz.py kernels|reference|halo <first seed> <count>` runs longer campaigns (DESIGN.md section 3 records one:
+`python tests/test_fuzz.py kernels|reference|halo|tables <first seed> <count>` runs longer campaigns (DESIGN.md section 3 records one:
 3000 + 3000 cases, no mismatch)."""
 import sys
 
@@ -149,18 +149,47 @@ def test_random_slab_layouts_need_only_the_promised_halo():
     assert not bad, bad[:3]
 
 
+
+def tables_vs_reference(ns, seed):
+    """build_tables_kernel (emulated) against the live reference's x_next_table, x_next_isok and cost table G."""
+    from oracle import ref_loader
+    from pyro_b200 import problem
+    from tests.cases import build_case
+    from tests.emu import emu
+    rng = np.random.default_rng(seed)
+    case = random_case(rng, tiny=True)
+    with ref_loader.quiet():
+        _, rgrid, _, rdp = ref_loader.build_reference(ns, case)
+    _, grid, cf = build_case(case)
+    P = problem.extract(grid, cf, case["alpha"])
+    xn, ok, G = emu.build_tables(P)
+    if np.array_equal(xn, rgrid.x_next_table) and np.array_equal(ok, rgrid.x_next_isok) and np.array_equal(G, rdp.G):
+        return []
+    return [(seed, int((xn != rgrid.x_next_table).sum()), int((ok != rgrid.x_next_isok).sum()), int((G != rdp.G).sum()), case)]
+
+
+@pytest.mark.filterwarnings("ignore::RuntimeWarning", "ignore::DeprecationWarning")
+def test_random_problems_table_builder_equals_the_live_reference_tables():
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("unmodified reference not present")
+    ns = ref_loader.load()
+    bad = [b for seed in range(9000, 9120) for b in tables_vs_reference(ns, seed)]
+    assert not bad, bad[:3]
+
+
 if __name__ == "__main__":
     import os
     import warnings
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     warnings.simplefilter("ignore")
     which, first, count = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
-    if which == "reference":
+    if which in ("reference", "tables"):
         from oracle import ref_loader
         ns = ref_loader.load()
     bad = []
     for seed in range(first, first + count):
-        bad += kernels_vs_oracle(seed) if which == "kernels" else halo_sufficiency(seed) if which == "halo" else oracle_vs_reference(ns, seed)
+        bad += kernels_vs_oracle(seed) if which == "kernels" else halo_sufficiency(seed) if which == "halo" else tables_vs_reference(ns, seed) if which == "tables" else oracle_vs_reference(ns, seed)
     print(f"{which}: seeds {first}..{first + count - 1}: {len(bad)} mismatching variants")
     for b in bad[:10]:
         print(b)

@@ -521,3 +521,17 @@ def test_mirror_planner_drops_in_on_the_real_pyro_objects_of_a_3d_example():
     with ref_loader.quiet():
         ref = ns.dynamicprogramming.LookUpTableController(grid, gold[f"pi_{k}"])
     assert np.array_equal(ctl.c(x, 0), ref.c(x, 0))
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_emulated_table_builder_equals_reference_tables(name):
+    """build_tables_kernel (pdp_build_tables) against the reference's own x_next_table / x_next_isok / G samples."""
+    case, gold = CASES[name], load_golden(name)
+    _, grid, cf = build_case(case)
+    P = problem.extract(grid, cf, case.get("alpha", 1.0))
+    xn, ok, G = emu.build_tables(P)
+    st = int(gold["table_stride"])
+    assert np.array_equal(xn[::st], gold["x_next_sample"]) and np.array_equal(ok[::st], gold["x_next_isok_sample"])
+    assert np.array_equal(G[::st], gold["G_sample"])
+    part = emu.build_tables(P, 7, 5)                                  # a node range
+    assert np.array_equal(part[0], xn[7:12]) and np.array_equal(part[2], G[7:12])
