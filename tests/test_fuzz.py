@@ -5,7 +5,7 @@
   * the C oracle against the LIVE unmodified reference (where it is importable: this container) after 1-3 sweeps of its
     DynamicProgrammingWithLookUpTable — bit for bit.  This widens the pin of the oracle beyond the committed fixtures.
 
-`python tests/test_fuzz.py kernels|reference|halo|tables <first seed> <count>` runs longer campaigns (DESIGN.md section 3 records one:
+`python tests/test_fuzz.py kernels|reference|halo|tables|rollouts|spline|lut <first seed> <count>` runs longer campaigns (DESIGN.md section 3 records one:
 3000 + 3000 cases, no mismatch)."""
 import sys
 
@@ -178,18 +178,150 @@ def test_random_problems_table_builder_equals_the_live_reference_tables():
     assert not bad, bad[:3]
 
 
+
+def rollouts_vs_reference(ns, seed, rtol=1e-8):
+    """rollout_kernel (emulated) against the live reference's closed-loop 'euler' simulation under its LookUpTableController,
+    with a RANDOM policy table (rough input tables: the interpolation conventions matter), random plant parameters,
+    initial states inside and outside the grid."""
+    from oracle import ref_loader
+    from pyro_b200 import problem
+    from tests.cases import build_case
+    from tests.emu import emu
+    rng = np.random.default_rng(seed)
+    case = random_case(rng, tiny=True)
+    case["x_grid_dim"] = [max(d, 3) for d in case["x_grid_dim"]]
+    case["cost"], case["alpha"] = "quadratic", 1.0
+    case.setdefault("Q", [1.0] * len(case["x_grid_dim"]))
+    case.setdefault("R", [1.0] * len(case["u_grid_dim"]))
+    with ref_loader.quiet():
+        rsys, rgrid, _, _ = ref_loader.build_reference(ns, case)
+        pi = rng.integers(0, rgrid.actions_n, rgrid.nodes_n)
+        ctl = ns.dynamicprogramming.LookUpTableController(rgrid, pi)
+        cl = ctl + rsys
+        npts, tf = int(rng.integers(5, 40)), float(rng.uniform(0.1, 1.0))
+        lo, hi = np.asarray(rsys.x_lb), np.asarray(rsys.x_ub)
+        x0s = rng.uniform(lo - 0.1 * (hi - lo), hi + 0.1 * (hi - lo), (4, rsys.n))
+        xs, us = [], []
+        for x0 in x0s:
+            cl.x0 = x0.copy()
+            traj = cl.compute_trajectory(tf, npts, 'euler')
+            xs.append(traj.x.copy()); us.append(traj.u.copy())
+    xs, us = np.array(xs), np.array(us)
+    sys_, grid, cf = build_case(case)
+    P = problem.extract(grid, cf, 1.0)
+    x, u = emu.rollout(P, pi, problem.plant_parameters(sys_, P.system_id), x0s, npts, tf / (npts - 1))
+    finite = np.isfinite(xs).all()
+    scale = max(1.0, np.abs(xs[np.isfinite(xs)]).max()) if np.isfinite(xs).any() else 1.0
+    if finite and scale < 1e6:      # trajectories that blow up (stiff random plants at large dt) amplify the last bit: not compared
+        if np.abs(x - xs).max() > rtol * scale or np.abs(u - us).max() > rtol * max(1.0, np.abs(us).max()):
+            return [(seed, float(np.abs(x - xs).max()), float(np.abs(u - us).max()), scale, case)]
+    return []
+
+
+def spline_vs_scipy(seed, rtol=1e-9):
+    """Host plan + fit kernels + sweep_lut_spline_kernel (emulated) on random tables and rough J against the oracle's scipy call."""
+    from oracle import np_oracle as npo
+    from pyro_b200 import problem
+    from tests.emu import emu
+    rng = np.random.default_rng(seed)
+    dims, A = [int(rng.integers(4, 30)), int(rng.integers(4, 30))], int(rng.integers(2, 9))
+    lb, ub = -rng.uniform(0.5, 5, 2), rng.uniform(0.5, 5, 2)
+    levels = [np.linspace(lb[i], ub[i], dims[i]) for i in range(2)]
+    N = dims[0] * dims[1]
+    X = np.stack([g.reshape(-1) for g in np.meshgrid(*levels, indexing="ij")], axis=1)
+    x_next = X[:, None, :] + rng.normal(0, 0.3 * (ub - lb) / np.array(dims), (N, A, 2)) * rng.choice([1.0, 5.0])
+    G = rng.uniform(0, 2, (N, A))
+    J0 = rng.uniform(0, 100, N)
+    alpha = float(rng.choice([1.0, 0.9]))
+
+    class Sys2:
+        n, m = 2, 1
+        x_lb, x_ub, u_lb, u_ub = lb, ub, np.array([-1.0]), np.array([1.0])
+
+    class Grid2:
+        sys, dt = Sys2(), 0.05
+        x_grid_dim, u_grid_dim = np.array(dims), np.array([A])
+        x_level, u_level = levels, [np.linspace(-1, 1, A)]
+
+    class Cost2:
+        INF = 1000.0
+    P = problem.extract(Grid2(), Cost2(), alpha)
+    J, pi, _, _ = emu.spline_sweep(P, J0, x_next, G)
+    Jr, pr, gap = npo.spline_sweep(levels, dims, J0, x_next, G, alpha)
+    scale = np.abs(Jr).max()
+    if np.abs(J - Jr).max() > rtol * scale or ((pi != pr) & (gap > 10 * rtol * scale)).any():
+        return [(seed, float(np.abs(J - Jr).max()), int((pi != pr).sum()), dims, A)]
+    return []
+
+
+def lut_vs_numpy(seed):
+    """sweep_lut_kernel / sweep_policy_kernel (emulated) for n = 2, 3, 4 on random tables against scipy's RGI (bit for bit)."""
+    from oracle import np_oracle as npo
+    from pyro_b200 import problem
+    from tests.emu import emu
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(2, 5))
+    dims = [int(rng.integers(2, 9 if n > 2 else 25)) for _ in range(n)]
+    A = int(rng.integers(1, 9))
+    lb, ub = -rng.uniform(0.5, 5, n), rng.uniform(0.5, 5, n)
+    levels = [np.linspace(lb[i], ub[i], dims[i]) for i in range(n)]
+    N = int(np.prod(dims))
+    X = np.stack([g.reshape(-1) for g in np.meshgrid(*levels, indexing="ij")], axis=1)
+    x_next = X[:, None, :] + rng.normal(0, 1.0, (N, A, n)) * (ub - lb) / np.array(dims)
+    x_next[::7, 0, :] = X[::7]                  # exact node hits
+    x_next[3::11, A - 1, n - 1] = ub[n - 1]     # exactly on the upper bound
+    G = np.where(rng.random((N, A)) < 0.1, 500.0, rng.uniform(0, 2, (N, A)))
+    J0 = rng.uniform(0, 100, N)
+    alpha = float(rng.choice([1.0, 0.97]))
+
+    class SysN:
+        m = 1
+        x_lb, x_ub, u_lb, u_ub = lb, ub, np.array([-1.0]), np.array([1.0])
+    SysN.n = n
+
+    class GridN:
+        sys, dt = SysN(), 0.05
+        x_grid_dim, u_grid_dim = np.array(dims), np.array([max(A, 1)])
+        x_level, u_level = levels, [np.linspace(-1, 1, max(A, 1))]
+
+    class CostN:
+        INF = 500.0
+    P = problem.extract(GridN(), CostN(), alpha, lut_actions=A if A == 1 else None)
+    J, pi, _ = emu.lut_sweep(P, J0, x_next, G)
+    Jr, pr = npo.lut_sweep(levels, dims, J0, x_next, G, alpha, use_scipy=True)
+    return [] if np.array_equal(J, Jr) and np.array_equal(pi, pr) else [(seed, n, dims, A, int((J != Jr).sum()), int((pi != pr).sum()))]
+
+
+@pytest.mark.filterwarnings("ignore::RuntimeWarning", "ignore::DeprecationWarning")
+def test_random_policies_rollout_kernel_equals_the_live_reference_simulation():
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("unmodified reference not present")
+    ns = ref_loader.load()
+    bad = [b for seed in range(11000, 11060) for b in rollouts_vs_reference(ns, seed)]
+    assert not bad, bad[:3]
+
+
+def test_random_tables_spline_and_lut_kernels_equal_scipy():
+    bad = [b for seed in range(12000, 12040) for b in spline_vs_scipy(seed)]
+    bad += [b for seed in range(13000, 13080) for b in lut_vs_numpy(seed)]
+    assert not bad, bad[:3]
+
+
 if __name__ == "__main__":
     import os
     import warnings
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     warnings.simplefilter("ignore")
     which, first, count = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
-    if which in ("reference", "tables"):
+    if which in ("reference", "tables", "rollouts"):
         from oracle import ref_loader
         ns = ref_loader.load()
     bad = []
     for seed in range(first, first + count):
-        bad += kernels_vs_oracle(seed) if which == "kernels" else halo_sufficiency(seed) if which == "halo" else tables_vs_reference(ns, seed) if which == "tables" else oracle_vs_reference(ns, seed)
+        bad += {"kernels": lambda: kernels_vs_oracle(seed), "halo": lambda: halo_sufficiency(seed), "tables": lambda: tables_vs_reference(ns, seed),
+                "rollouts": lambda: rollouts_vs_reference(ns, seed), "spline": lambda: spline_vs_scipy(seed), "lut": lambda: lut_vs_numpy(seed),
+                "reference": lambda: oracle_vs_reference(ns, seed)}[which]()
     print(f"{which}: seeds {first}..{first + count - 1}: {len(bad)} mismatching variants")
     for b in bad[:10]:
         print(b)
