@@ -510,7 +510,7 @@ def run_workload(ctx, args, wl_key, primary):
         kernel_ms = ctx.reduce([float(np.median(km))], "max")[0]
         exchange_ms = ctx.reduce([float(np.median(xm))], "max")[0]
 
-    # ---- roofline: the unit that binds (ncu, profiles/) — FP64 issue for the 2-D kernel, the L1 data pipe for the 4-D
+    # ---- roofline: the unit that binds (ncu, profiles/) — the FP64 pipe for the 2-D kernel, the L1 data pipe for the 4-D
     #      gathers — evaluated on THIS run's kernel time; the SURVEY 8(d) HBM contract figure and DRAM traffic beside it ----
     peak_hbm, peak_src = measured_peak()
     slab_evals = evals_per_step / world

@@ -118,9 +118,9 @@ __device__ __forceinline__ void stage(double* dst, const double* __restrict__ sr
 //   v00*(1-y0), v01*(1-y0), v10*y0, v11*y0      (first factor pair of evaluate_linear_2d's terms)
 // stay in registers until x_next[1] leaves the cell: the common action costs 19 FP64 issues (17.5 in the
 // MONO loop), one LDS and no global load; leaving the cell re-runs the table-checked search and four
-// gathers.  An FP64 instruction holds the SM sub-partition's issue port for two cycles (measured,
-// scripts/micro/fp64_peak.cu), so the kernel's cost is 2*FP64 + other instructions per warp: ncu r01K
-// counts 19.45 + 18.63 per warp-eval = 57.5 cycles, and the measured 0.312 ms/sweep at cfg 2 IS 57.7 cycles.
+// gathers.  What binds the kernel is the FP64 pipe (68 % of its peak rate, ncu r01K / r02m) — not the issue port, as
+// round 1's count model had it (2*FP64 + other instructions = 57.5 "issue cycles" against 57.7 measured was a
+// coincidence: see the A/B under MONO below).
 // =================================================================================================
 // MONO = the host verified that x_next[1] cannot decrease along the action list (B.u ascending,
 // inv(H) > 0, dt > 0, every action allowed — the linspace input grid of a pendulum): then lo <= x
