@@ -343,6 +343,8 @@ class DynamicProgramming:
         eng = self._engine
         if eng is None or not hasattr(eng, "rollout"):
             raise NotImplementedError("closed-loop rollouts need the policy on one device handle (not a sharded / multi-part run)")
+        if int(n) < 2 or not tf > 0:
+            raise ValueError("compute_closed_loop_trajectories: needs n >= 2 points and tf > 0")
         phys = _problem.plant_parameters(self.sys, eng.problem.system_id)
         dt = (tf + 0.0 - 0) / (n - 1)
         x, u = eng.rollout(phys, x0, n, dt, stride)

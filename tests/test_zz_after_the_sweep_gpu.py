@@ -46,6 +46,8 @@ def test_rollout_argument_errors():
         dp.compute_closed_loop_trajectories(np.zeros((3, 4)), 1.0, 11)      # wrong state dimension
     with pytest.raises(ValueError):
         dp._engine.rollout(np.zeros(16), np.zeros((1, 2)), 0, 0.1)           # npts < 1
+    with pytest.raises(ValueError):
+        dp.compute_closed_loop_trajectories(np.zeros((1, 2)), 1.0, 1)       # one point: no step size
 
 
 # ---- DynamicProgramming2DRectBivariateSpline (pdp_set_interpolant, spline.cuh) ---------------------------------------
