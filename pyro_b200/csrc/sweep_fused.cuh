@@ -343,8 +343,6 @@ sweep_pendulum_kernel(const __grid_constant__ DevProblem P, const double* __rest
             return oob ? INF : Q;
         };
         hi = live ? -PINF : PINF;   // live lanes: no cell yet, the first action locates it
-        // Loop nest: the inner loop runs the pairs the cached cell still covers for every lane of the warp (the cell
-        // state is loop-invariant there); the outer loop handles the pair at which some lane leaves its cell.
         // The action records are walked by ADDRESS (one add per pair; the argmin remembers the address of its record).
         const smem_addr_t act0 = smem_addr_of(s_act);
         const smem_addr_t pend = act0 + 16u * (unsigned)A_pad;
