@@ -535,3 +535,16 @@ def test_emulated_table_builder_equals_reference_tables(name):
     assert np.array_equal(G[::st], gold["G_sample"])
     part = emu.build_tables(P, 7, 5)                                  # a node range
     assert np.array_equal(part[0], xn[7:12]) and np.array_equal(part[2], G[7:12])
+
+
+def test_emulated_pendulum_kernel_at_full_size_config2_equals_c_oracle_on_every_node():
+    """BASELINE config 2 (SinglePendulum 1001 x 1001 x 201, 2.0e8 evals) through the shipped kernel under the emulator: all
+    1 002 001 nodes against the C oracle, rough J (about 25 s)."""
+    case = dict(system="SinglePendulum", x_grid_dim=[1001, 1001], u_grid_dim=[201], xbar=[-3.14, 0.0], INF=300.0)
+    _, grid, cf = build_case(case)
+    P = problem.extract(grid, cf, 1.0)
+    J0 = np.random.default_rng(1).uniform(0, 250, P.N)
+    J, pi, st = emu.sweep(P, J0, lanes=1)
+    Jr, pr = c_oracle.sweep_fused(P, J0)
+    assert np.array_equal(J, Jr) and np.array_equal(pi, pr)
+    assert st[0] == Jr.max() and st[1] == (Jr - J0).max() and st[2] == (Jr - J0).min()

@@ -226,7 +226,7 @@ def test_pendulum_loop_nest_and_pair_loop_on_edge_shapes(loop, monkeypatch):
 
 
 def test_full_size_config2_sampled_against_oracle_and_properties():
-    """BASELINE config 2 (SinglePendulum 1001x1001x201) at full size: random node ranges against the C
+    """BASELINE config 2 (SinglePendulum 1001x1001x201) at full size: all 1 002 001 nodes against the C
     oracle, plus size-independent properties (determinism, monotonicity of the Bellman operator,
     constant-shift equivariance for alpha = 1 on nodes whose minimiser is a valid transition)."""
     case = dict(system="SinglePendulum", x_grid_dim=[1001, 1001], u_grid_dim=[201], xbar=[-3.14, 0.0], INF=300.0)
@@ -238,9 +238,8 @@ def test_full_size_config2_sampled_against_oracle_and_properties():
     eng.set_J(J0)
     eng.sweep(1)
     J1, pi1 = eng.get_J(), eng.get_pi()
-    for lo in list(rng.integers(0, P.N - 512, 24)) + [0, P.N - 512, 1001 * 500]:
-        Jr, pr = c_oracle.sweep_fused(P, J0, int(lo), int(lo) + 512)
-        assert np.array_equal(J1[lo:lo + 512], Jr) and np.array_equal(pi1[lo:lo + 512], pr)
+    Jr, pr = c_oracle.sweep_fused(P, J0)                     # EVERY node: the oracle needs a second or two for 2e8 evals
+    assert np.array_equal(J1, Jr) and np.array_equal(pi1, pr), (int((J1 != Jr).sum()), int((pi1 != pr).sum()))
     # determinism
     eng.set_J(J0)
     eng.sweep(1)
